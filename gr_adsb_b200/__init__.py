@@ -1,0 +1,15 @@
+"""gr-adsb_b200: the ADS-B burst-detect + PPM-demod path of gr-adsb, on a B200.
+
+`framer` and `demod` mirror `gnuradio.adsb.framer` / `gnuradio.adsb.demod`
+(python/adsb/__init__.py:24-25); `Context` is the raw ctypes handle onto `include/adsb_b200.h`.
+"""
+from ._native import Context, AdsbError, HIT_DTYPE, unpack_bits, build, lib  # noqa: F401
+from ._native import HIT_DEMOD_VALID, HIT_CRC_OK, HIT_LATE_TAG  # noqa: F401
+
+
+def __getattr__(name):
+    # blocks import lazily: they need the native library, `synth` and the ABI constants do not
+    if name in ("framer", "demod"):
+        from . import blocks
+        return getattr(blocks, name)
+    raise AttributeError(name)

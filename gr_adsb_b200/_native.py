@@ -1,0 +1,233 @@
+"""ctypes binding of the C ABI in `include/adsb_b200.h` (built into `csrc/libadsb_b200.so`).
+
+There is no CPU fallback: if the shared library or a B200 is missing, creating a context raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libadsb_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "adsb_b200.h")
+
+ADSB_OK = 0
+E_CAPACITY = -4
+HIT_DEMOD_VALID = 0x1
+HIT_CRC_OK = 0x2
+HIT_LATE_TAG = 0x4
+
+HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
+assert HIT_DTYPE.itemsize == 32
+
+
+class Counters(C.Structure):
+    _fields_ = [("n_samples", C.c_uint64), ("n_candidates", C.c_uint64), ("n_hits", C.c_uint64),
+                ("n_demod", C.c_uint64), ("n_crc_ok", C.c_uint64), ("last_pulse", C.c_int64),
+                ("any_rise", C.c_uint32), ("any_fall", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libadsb_b200.so (in-tree, so it travels with the repo)."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs.append(HEADER)
+    if not force and os.path.isfile(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(CSRC, "adsb_api.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_create", "adsb_destroy",
+           "adsb_last_error", "adsb_reset_state", "adsb_get_state", "adsb_set_state", "adsb_get_counters",
+           "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish"]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i64, f32, i32 = C.c_void_p, C.c_size_t, C.c_int64, C.c_float, C.c_int
+    L.adsb_strerror.restype = C.c_char_p
+    L.adsb_strerror.argtypes = [i32]
+    L.adsb_abi_version.restype = i32
+    L.adsb_device_count.restype = i32
+    L.adsb_create.restype = i32
+    L.adsb_create.argtypes = [C.POINTER(vp), i32, i32, sz]
+    L.adsb_destroy.restype = None
+    L.adsb_destroy.argtypes = [vp]
+    L.adsb_last_error.restype = C.c_char_p
+    L.adsb_last_error.argtypes = [vp]
+    L.adsb_reset_state.restype = i32
+    L.adsb_reset_state.argtypes = [vp]
+    L.adsb_get_state.restype = i32
+    L.adsb_get_state.argtypes = [vp, C.POINTER(f32), C.POINTER(i64)]
+    L.adsb_set_state.restype = i32
+    L.adsb_set_state.argtypes = [vp, f32, i64]
+    L.adsb_get_counters.restype = i32
+    L.adsb_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    L.adsb_framer_work.restype = i32
+    L.adsb_framer_work.argtypes = [vp, vp, sz, sz, f32, vp, vp, sz, C.POINTER(sz)]
+    L.adsb_demod_work.restype = i32
+    L.adsb_demod_work.argtypes = [vp, vp, sz, vp, sz, vp, vp]
+    L.adsb_burst_work.restype = i32
+    L.adsb_burst_work.argtypes = [vp, vp, i32, sz, sz, sz, f32, i64, vp, sz, C.POINTER(sz)]
+    L.adsb_burst_work_dev.restype = i32
+    L.adsb_burst_work_dev.argtypes = [vp, vp, i32, sz, sz, sz, sz, f32, i64, i64, vp, C.POINTER(vp)]
+    L.adsb_burst_finish.restype = i32
+    L.adsb_burst_finish.argtypes = [vp, C.POINTER(Counters), vp, sz, C.POINTER(sz)]
+    _lib = L
+    return L
+
+
+class AdsbError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = lib().adsb_strerror(code).decode()
+        RuntimeError.__init__(self, "adsb_b200: %s (%d)%s" % (msg, code, (": " + detail) if detail else ""))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context(object):
+    """One `adsb_ctx`: device buffers + the framer state of one block instance."""
+
+    def __init__(self, sps, max_items, device=0):
+        self._h = C.c_void_p()
+        self.sps = int(sps)
+        self.hist = 8 * self.sps - 1
+        self.max_items = int(max_items)
+        self.device = int(device)
+        rc = lib().adsb_create(C.byref(self._h), self.device, self.sps, self.max_items)
+        if rc != ADSB_OK:
+            self._h = C.c_void_p()
+            raise AdsbError(rc, "adsb_create(device=%d, sps=%d, max_items=%d)" % (device, sps, max_items))
+
+    def close(self):
+        if self._h:
+            lib().adsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != ADSB_OK:
+            raise AdsbError(rc, lib().adsb_last_error(self._h).decode())
+
+    # --- state ---------------------------------------------------------------------------
+    def reset_state(self):
+        self._check(lib().adsb_reset_state(self._h))
+
+    def get_state(self):
+        a, b = C.c_float(), C.c_int64()
+        self._check(lib().adsb_get_state(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_state(self, prev_in0, prev_eob_idx):
+        self._check(lib().adsb_set_state(self._h, float(prev_in0), int(prev_eob_idx)))
+
+    def counters(self):
+        c = Counters()
+        self._check(lib().adsb_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    # --- block entry points -----------------------------------------------------------------
+    def framer_work(self, in0, n_out, threshold):
+        """-> (window indices int64[], snr float32[])"""
+        in0 = np.ascontiguousarray(in0, dtype=np.float32)
+        cap = int(n_out) // (63 * self.sps) + 2
+        idx = np.empty(cap, np.int64)
+        snr = np.empty(cap, np.float32)
+        n = C.c_size_t(0)
+        self._check(lib().adsb_framer_work(self._h, _ptr(in0), len(in0), int(n_out), float(np.float32(threshold)),
+                                           _ptr(idx), _ptr(snr), cap, C.byref(n)))
+        return idx[:n.value], snr[:n.value]
+
+    def demod_work(self, in0, sob_idx):
+        """-> (bits uint8[n_tags,112], valid uint8[n_tags])"""
+        in0 = np.ascontiguousarray(in0, dtype=np.float32)
+        sob = np.ascontiguousarray(sob_idx, dtype=np.int64)
+        bits = np.zeros((len(sob), 112), np.uint8)
+        valid = np.zeros(len(sob), np.uint8)
+        self._check(lib().adsb_demod_work(self._h, _ptr(in0), len(in0), _ptr(sob), len(sob), _ptr(bits), _ptr(valid)))
+        return bits, valid
+
+    def burst_work(self, buf, n_out=None, lead=None, threshold=0.01, base=0, cap=None):
+        """Fused path over a host buffer (float32 |IQ|^2 or complex64 IQ) -> structured hits array."""
+        buf = np.ascontiguousarray(buf)
+        if buf.dtype == np.complex64:
+            c64 = 1
+        elif buf.dtype == np.float32:
+            c64 = 0
+        else:
+            raise TypeError("burst_work takes float32 or complex64")
+        n_in = len(buf)
+        if lead is None:
+            lead = self.hist if n_out is None else int(n_out) + self.hist - n_in
+        if n_out is None:
+            n_out = n_in + lead - self.hist
+        cap = cap or (int(n_out) // (63 * self.sps) + 2)
+        hits = np.zeros(cap, HIT_DTYPE)
+        n = C.c_size_t(0)
+        self._check(lib().adsb_burst_work(self._h, _ptr(buf), c64, n_in, int(lead), int(n_out),
+                                          float(np.float32(threshold)), int(base), _ptr(hits), cap, C.byref(n)))
+        return hits[:n.value]
+
+    def burst_work_ptr(self, host_ptr, c64, n_in, n_out, lead, threshold, base, hits):
+        """Same, raw host pointer + caller-owned hits array (bench.py's end-to-end leg)."""
+        n = C.c_size_t(0)
+        self._check(lib().adsb_burst_work(self._h, C.c_void_p(host_ptr), int(c64), int(n_in), int(lead), int(n_out),
+                                          float(np.float32(threshold)), int(base), _ptr(hits), len(hits), C.byref(n)))
+        return n.value
+
+    def burst_work_dev(self, dev_ptr, c64, n_in, n_out, lead, threshold, base=0, eob_in=-1, halo_left=0, stream=0):
+        """Device-resident input; asynchronous.  Returns the device pointer of the hit records."""
+        out = C.c_void_p()
+        self._check(lib().adsb_burst_work_dev(self._h, C.c_void_p(dev_ptr), int(c64), int(n_in), int(lead), int(n_out),
+                                              int(halo_left), float(np.float32(threshold)), int(base), int(eob_in),
+                                              C.c_void_p(stream), C.byref(out)))
+        return out.value
+
+    def burst_finish(self, fetch_hits=True, cap=None):
+        c = Counters()
+        n = C.c_size_t(0)
+        if not fetch_hits:
+            self._check(lib().adsb_burst_finish(self._h, C.byref(c), None, 0, C.byref(n)))
+            return c.as_dict(), None
+        cap = cap or 1 << 16
+        while True:
+            hits = np.zeros(cap, HIT_DTYPE)
+            rc = lib().adsb_burst_finish(self._h, C.byref(c), _ptr(hits), cap, C.byref(n))
+            if rc == E_CAPACITY:
+                raise AdsbError(rc, "burst_finish: pass cap >= %d" % n.value)
+            self._check(rc)
+            return c.as_dict(), hits[:n.value]
+
+
+def unpack_bits(hits):
+    """hits['bits'] (packed, MSB first) -> uint8[n,112]"""
+    if len(hits) == 0:
+        return np.zeros((0, 112), np.uint8)
+    return np.unpackbits(np.ascontiguousarray(hits["bits"]), axis=1)[:, :112]

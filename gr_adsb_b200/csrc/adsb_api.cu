@@ -1,0 +1,627 @@
+// C ABI (include/adsb_b200.h) over the sm_100a kernels.  No torch types, no exceptions.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/adsb_b200.h"
+#include "adsb_device.cuh"
+#include "adsb_resolve.cuh"
+#include "adsb_scan.cuh"
+
+using namespace adsb;
+
+static_assert(sizeof(adsb_hit) == sizeof(Rec), "adsb_hit layout");
+
+namespace {
+
+constexpr int kFirstHits = 64;          // hits fetched together with the header
+constexpr size_t kPipeChunk = 1u << 22; // items per H2D chunk on the host fused path
+constexpr int kEvRing = 4;
+
+__global__ void init_header_kernel(Header *h)
+{
+    memset(h, 0, sizeof(Header));
+    h->last_pulse = -1;
+    h->last_accept = -1;
+}
+
+struct HostStage {
+    Header hdr;
+    Rec first[kFirstHits];
+};
+
+}  // namespace
+
+struct adsb_ctx {
+    int device, sps, T, rh, hist;
+    size_t max_items;
+    float prev_in0;
+    long long prev_eob;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t ev[kEvRing];
+    void *d_in;
+    size_t d_in_bytes;
+    Rec *d_cand, *d_ord, *d_hits;
+    unsigned cand_cap, hit_cap;
+    uint2 *d_tile_tab;
+    size_t tile_cap;
+    unsigned long long *d_status_g, *d_status_c;
+    size_t status_g_n, status_c_n;
+    Header *d_hdr;
+    unsigned *d_crc;
+    long long *d_sob;
+    unsigned char *d_bits, *d_valid;
+    size_t tag_cap;
+    HostStage *h_stage;
+    unsigned epoch;
+    int num_sms;
+    // bookkeeping of the call in flight (adsb_burst_work_dev -> adsb_burst_finish)
+    struct {
+        bool pending;
+        long long n_out, lead, base, eob_in;
+        int left_is_start;
+        cudaStream_t stream;
+    } last;
+    adsb_counters counters;
+    char err[256];
+};
+
+namespace {
+
+int fail(adsb_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        if (e != cudaSuccess)
+            snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+        else
+            snprintf(c->err, sizeof(c->err), "%s", what);
+    }
+    return code;
+}
+
+#define CK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return fail(ctx, ADSB_E_CUDA, #call, e_);  \
+    } while (0)
+
+void crc_table(unsigned *t)
+{
+    // t[i] = x^(111-i) mod g, g = 0x1FFF409 (decoder.py:269)
+    unsigned r = 1;
+    for (int i = kMsgBits - 1; i >= 0; i--) {
+        t[i] = r;
+        r <<= 1;
+        if (r & (1u << 24)) r ^= 0x1FFF409u;
+    }
+}
+
+template <int T, int HS, bool C64>
+cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s)
+{
+    const size_t smem = tile_smem_bytes(T, P.rh);
+    static bool configured = false;   // per instantiation; one device per process in practice
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<T, HS, C64>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    scan_slice_kernel<T, HS, C64><<<n_blocks, kThreads, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P, bool c64, unsigned n_blocks, cudaStream_t s)
+{
+    if (n_blocks == 0) return cudaSuccess;
+    if (c->T == 4096) {
+        if (c->sps == 2) return c64 ? launch_scan_t<4096, 1, true>(P, n_blocks, s) : launch_scan_t<4096, 1, false>(P, n_blocks, s);
+        return c64 ? launch_scan_t<4096, 0, true>(P, n_blocks, s) : launch_scan_t<4096, 0, false>(P, n_blocks, s);
+    }
+    if (c->sps == 8) return c64 ? launch_scan_t<8192, 4, true>(P, n_blocks, s) : launch_scan_t<8192, 4, false>(P, n_blocks, s);
+    return c64 ? launch_scan_t<8192, 0, true>(P, n_blocks, s) : launch_scan_t<8192, 0, false>(P, n_blocks, s);
+}
+
+long long tiles_for(const adsb_ctx *c, long long n_out, long long lead)
+{
+    if (n_out <= lead) return 0;
+    return (n_out - lead + c->T - 1) / c->T;
+}
+
+// Validate the geometry shared by every fused entry point.
+int check_geometry(adsb_ctx *ctx, size_t n_in, size_t lead, size_t n_out, size_t halo_left)
+{
+    if (n_out == 0 || n_in == 0) return fail(ctx, ADSB_E_INVAL, "empty call");
+    if (lead + n_in != n_out + (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "lead + n_in must equal n_out + 8*sps - 1");
+    if (n_in > ctx->max_items) return fail(ctx, ADSB_E_INVAL, "n_in exceeds max_items given to adsb_create");
+    if (lead != 0 && lead != (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "lead must be 0 or 8*sps - 1");
+    if (halo_left != 0 && (halo_left < 256 || lead != 0)) return fail(ctx, ADSB_E_INVAL, "halo_left must be 0 or >= 256 with lead 0");
+    return ADSB_OK;
+}
+
+ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t lead, size_t n_out, size_t halo_left,
+                       float thr, long long base, int prev_bit, int do_demod)
+{
+    ScanParams P;
+    memset(&P, 0, sizeof(P));
+    P.in = d_in;
+    P.n_arr = (long long)n_in;
+    P.lead = (long long)lead;
+    P.n_loc = (long long)(lead + n_in);
+    P.own_lo = (long long)halo_left;
+    P.own_hi = (long long)n_out;
+    P.base = base;
+    P.n_tiles_total = tiles_for(c, (long long)n_out, (long long)lead);
+    P.thr = thr;
+    P.sps = c->sps;
+    P.rh = c->rh;
+    P.left_is_start = halo_left == 0;
+    P.prev_bit = prev_bit;
+    P.do_demod = do_demod;
+    P.hist = c->hist;
+    P.cand = c->d_cand;
+    P.cand_cap = c->cand_cap;
+    P.tile_tab = c->d_tile_tab;
+    P.hdr = c->d_hdr;
+    P.crc_tab = c->d_crc;
+    return P;
+}
+
+int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long eob_in, cudaStream_t s)
+{
+    ResolveParams R;
+    memset(&R, 0, sizeof(R));
+    R.tile_tab = ctx->d_tile_tab;
+    R.n_tiles = n_tiles;
+    R.cand = ctx->d_cand;
+    R.ord = ctx->d_ord;
+    R.hits = ctx->d_hits;
+    R.hit_cap = ctx->hit_cap;
+    R.cand_cap = ctx->cand_cap;
+    R.status_g = ctx->d_status_g;
+    R.status_c = ctx->d_status_c;
+    R.hdr = ctx->d_hdr;
+    R.epoch = ctx->epoch;
+    R.base = base;
+    R.eob_in = eob_in;
+    R.blank = 63 * ctx->sps;
+    if (n_tiles <= 0) return ADSB_OK;
+    const long long gchunks = (n_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
+    const unsigned cap_blocks = (unsigned)ctx->num_sms * 4u;
+    unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
+    gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
+    chain_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
+    compact_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
+    CK(cudaGetLastError());
+    return ADSB_OK;
+}
+
+int begin_call(adsb_ctx *ctx, cudaStream_t s)
+{
+    ctx->epoch = (ctx->epoch + 1) & 0x3fffffffu;
+    if (ctx->epoch == 0) {   // wrapped: stale status words could alias, clear them
+        CK(cudaMemsetAsync(ctx->d_status_g, 0, ctx->status_g_n * 8, s));
+        CK(cudaMemsetAsync(ctx->d_status_c, 0, ctx->status_c_n * 8, s));
+        ctx->epoch = 1;
+    }
+    init_header_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
+    CK(cudaGetLastError());
+    return ADSB_OK;
+}
+
+int ensure_input(adsb_ctx *ctx, size_t bytes)
+{
+    if (ctx->d_in_bytes >= bytes) return ADSB_OK;
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    ctx->d_in = nullptr;
+    ctx->d_in_bytes = 0;
+    size_t want = ctx->max_items * 8 + 256;
+    if (want < bytes) want = bytes;
+    cudaError_t e = cudaMalloc(&ctx->d_in, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&ctx->d_in, want);
+    }
+    if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, "cudaMalloc(input staging)", e);
+    ctx->d_in_bytes = want;
+    return ADSB_OK;
+}
+
+// framer.py:121-123,165,177-179 -- advance prev_eob_idx from the call's summary
+long long next_eob(const Header &h, long long eob_in, long long n_out, int sps)
+{
+    if (!((h.flags & kFlagRise) && (h.flags & kFlagFall))) return eob_in;   // framer.py:95 guard
+    long long e = (h.last_accept >= 0) ? h.last_accept + 63LL * sps : eob_in;
+    if (h.last_pulse >= 0 && h.last_pulse > e) e = -1;    // a later pulse reset it (framer.py:121-123)
+    if (e >= n_out) e -= n_out;                            // framer.py:177-179
+    return e;
+}
+
+int status_of(adsb_ctx *ctx, const Header &h)
+{
+    if (h.flags & kFlagSpin) return fail(ctx, ADSB_E_INTERNAL, "look-back spin limit hit");
+    if (h.flags & kFlagHalo) return fail(ctx, ADSB_E_HALO, "pulse run crosses the left halo edge");
+    if (h.flags & (kFlagCandOverflow | kFlagHitOverflow)) return fail(ctx, ADSB_E_NOMEM, "candidate capacity exceeded (raise max_items)");
+    return ADSB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *adsb_strerror(int code)
+{
+    switch (code) {
+    case ADSB_OK: return "ok";
+    case ADSB_E_INVAL: return "invalid argument";
+    case ADSB_E_CUDA: return "CUDA runtime error";
+    case ADSB_E_NOMEM: return "out of memory / capacity";
+    case ADSB_E_CAPACITY: return "output capacity too small";
+    case ADSB_E_NODEVICE: return "no usable sm_100 CUDA device";
+    case ADSB_E_HALO: return "pulse run crosses the left halo of a shard";
+    case ADSB_E_INTERNAL: return "internal error";
+    default: return "unknown error";
+    }
+}
+
+int adsb_abi_version(void) { return ADSB_B200_ABI_VERSION; }
+
+int adsb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *adsb_last_error(const adsb_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+void adsb_destroy(adsb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_in);
+    cudaFree(ctx->d_cand);
+    cudaFree(ctx->d_ord);
+    cudaFree(ctx->d_hits);
+    cudaFree(ctx->d_tile_tab);
+    cudaFree(ctx->d_status_g);
+    cudaFree(ctx->d_status_c);
+    cudaFree(ctx->d_hdr);
+    cudaFree(ctx->d_crc);
+    cudaFree(ctx->d_sob);
+    cudaFree(ctx->d_bits);
+    cudaFree(ctx->d_valid);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < kEvRing; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
+{
+    if (!out) return ADSB_E_INVAL;
+    *out = nullptr;
+    if (sps < 2 || sps > 32 || (sps & 1) || max_items == 0) return ADSB_E_INVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ADSB_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return ADSB_E_NODEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return ADSB_E_NODEVICE;
+
+    adsb_ctx *ctx = new (std::nothrow) adsb_ctx();
+    if (!ctx) return ADSB_E_NOMEM;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sps = sps;
+    ctx->hist = 8 * sps - 1;
+    ctx->T = (sps <= 4) ? 4096 : 8192;
+    ctx->rh = ((120 * sps + 31) / 32) * 32;
+    ctx->max_items = max_items;
+    ctx->prev_in0 = 0.0f;
+    ctx->prev_eob = -1;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->err[0] = 0;
+
+    auto die = [&](int code, const char *what, cudaError_t e) {
+        char msg[256];
+        snprintf(msg, sizeof(msg), "%s: %s", what, cudaGetErrorString(e));
+        adsb_destroy(ctx);
+        fprintf(stderr, "adsb_create: %s\n", msg);
+        return code;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return die(ADSB_E_CUDA, "stream", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return die(ADSB_E_CUDA, "stream", e);
+    for (int i = 0; i < kEvRing; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return die(ADSB_E_CUDA, "event", e);
+
+    // candidates: at most one per 2 samples in theory, ~1 per 600 on busy air; size for 1 per 16.
+    size_t cap = max_items / 16 + 4096;
+    if (cap > 0x7fffff00u) cap = 0x7fffff00u;
+    ctx->cand_cap = (unsigned)cap;
+    ctx->hit_cap = (unsigned)cap;
+    ctx->tile_cap = max_items / ctx->T + 4;
+    ctx->status_g_n = ctx->tile_cap / kTilesPerChunk + 4;
+    ctx->status_c_n = cap / kThreads + 4;
+    ctx->tag_cap = 4096;
+#define ALLOC(ptr, bytes)                                                                       \
+    if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return die(ADSB_E_NOMEM, #ptr, e)
+    ALLOC(ctx->d_cand, cap * sizeof(Rec));
+    ALLOC(ctx->d_ord, cap * sizeof(Rec));
+    ALLOC(ctx->d_hits, cap * sizeof(Rec));
+    ALLOC(ctx->d_tile_tab, ctx->tile_cap * sizeof(uint2));
+    ALLOC(ctx->d_status_g, ctx->status_g_n * 8);
+    ALLOC(ctx->d_status_c, ctx->status_c_n * 8);
+    ALLOC(ctx->d_hdr, sizeof(Header));
+    ALLOC(ctx->d_crc, kMsgBits * sizeof(unsigned));
+    ALLOC(ctx->d_sob, ctx->tag_cap * sizeof(long long));
+    ALLOC(ctx->d_bits, ctx->tag_cap * kMsgBits);
+    ALLOC(ctx->d_valid, ctx->tag_cap);
+#undef ALLOC
+    if ((e = cudaMallocHost((void **)&ctx->h_stage, sizeof(HostStage))) != cudaSuccess) return die(ADSB_E_NOMEM, "pinned stage", e);
+    unsigned tab[kMsgBits];
+    crc_table(tab);
+    if ((e = cudaMemcpy(ctx->d_crc, tab, sizeof(tab), cudaMemcpyHostToDevice)) != cudaSuccess) return die(ADSB_E_CUDA, "crc table", e);
+    if ((e = cudaMemset(ctx->d_status_g, 0, ctx->status_g_n * 8)) != cudaSuccess) return die(ADSB_E_CUDA, "memset", e);
+    if ((e = cudaMemset(ctx->d_status_c, 0, ctx->status_c_n * 8)) != cudaSuccess) return die(ADSB_E_CUDA, "memset", e);
+    *out = ctx;
+    return ADSB_OK;
+}
+
+int adsb_reset_state(adsb_ctx *ctx)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    ctx->prev_in0 = 0.0f;
+    ctx->prev_eob = -1;
+    return ADSB_OK;
+}
+
+int adsb_get_state(const adsb_ctx *ctx, float *prev_in0, int64_t *prev_eob_idx)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    if (prev_in0) *prev_in0 = ctx->prev_in0;
+    if (prev_eob_idx) *prev_eob_idx = ctx->prev_eob;
+    return ADSB_OK;
+}
+
+int adsb_set_state(adsb_ctx *ctx, float prev_in0, int64_t prev_eob_idx)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    ctx->prev_in0 = prev_in0;
+    ctx->prev_eob = prev_eob_idx;
+    return ADSB_OK;
+}
+
+int adsb_get_counters(const adsb_ctx *ctx, adsb_counters *out)
+{
+    if (!ctx || !out) return ADSB_E_INVAL;
+    *out = ctx->counters;
+    return ADSB_OK;
+}
+
+int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in, size_t lead, size_t n_out,
+                        size_t halo_left, float threshold, int64_t base, int64_t eob_in, void *stream,
+                        const adsb_hit **d_hits)
+{
+    if (!ctx || !d_in) return ADSB_E_INVAL;
+    int rc = check_geometry(ctx, n_in, lead, n_out, halo_left);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const int prev_bit = (lead != 0) ? (0.0f >= threshold) : (ctx->prev_in0 >= threshold);
+    const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
+    if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
+    if ((rc = begin_call(ctx, s))) return rc;
+    ScanParams P = make_params(ctx, d_in, n_in, lead, n_out, halo_left, threshold, base, prev_bit, 1);
+    CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)n_tiles, s));
+    if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
+    ctx->last.pending = true;
+    ctx->last.n_out = (long long)n_out;
+    ctx->last.lead = (long long)lead;
+    ctx->last.base = base;
+    ctx->last.eob_in = eob_in;
+    ctx->last.left_is_start = halo_left == 0;
+    ctx->last.stream = s;
+    if (d_hits) *d_hits = reinterpret_cast<const adsb_hit *>(ctx->d_hits);
+    return ADSB_OK;
+}
+
+int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits)
+{
+    if (!ctx || !ctx->last.pending) return ADSB_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->last.stream;
+    CK(cudaMemcpyAsync(&ctx->h_stage->hdr, ctx->d_hdr, sizeof(Header), cudaMemcpyDeviceToHost, s));
+    if (hits && cap)
+        CK(cudaMemcpyAsync(ctx->h_stage->first, ctx->d_hits, sizeof(Rec) * kFirstHits, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->last.pending = false;
+    const Header &h = ctx->h_stage->hdr;
+    int rc = status_of(ctx, h);
+    if (rc) return rc;
+    adsb_counters &c = ctx->counters;
+    c.n_samples = (uint64_t)ctx->last.n_out;
+    c.n_candidates = h.n_cand;
+    c.n_hits = h.n_hits;
+    c.n_demod = h.n_demod;
+    c.n_crc_ok = h.n_crc;
+    c.last_pulse = h.last_pulse;
+    c.any_rise = (h.flags & kFlagRise) ? 1u : 0u;
+    c.any_fall = (h.flags & kFlagFall) ? 1u : 0u;
+    if (counters) *counters = c;
+    if (n_hits) *n_hits = (size_t)h.n_hits;
+    if (ctx->last.left_is_start) {
+        // advance the carried state (framer.py:87,121-123,165,177-179)
+        ctx->prev_eob = next_eob(h, ctx->last.eob_in, ctx->last.n_out, ctx->sps);
+        ctx->prev_in0 = (ctx->last.n_out - 1 >= ctx->last.lead) ? h.x_last : 0.0f;
+    }
+    if (hits) {
+        if (h.n_hits > cap) return fail(ctx, ADSB_E_CAPACITY, "hit capacity too small");
+        const size_t n = (size_t)h.n_hits;
+        const size_t nf = n < (size_t)kFirstHits ? n : (size_t)kFirstHits;
+        memcpy(hits, ctx->h_stage->first, nf * sizeof(Rec));
+        if (n > nf)
+            CK(cudaMemcpy(hits + nf, ctx->d_hits + nf, (n - nf) * sizeof(Rec), cudaMemcpyDeviceToHost));
+    }
+    return ADSB_OK;
+}
+
+int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size_t lead, size_t n_out,
+                    float threshold, int64_t base, adsb_hit *hits, size_t cap, size_t *n_hits)
+{
+    if (!ctx || !in) return ADSB_E_INVAL;
+    int rc = check_geometry(ctx, n_in, lead, n_out, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t isz = is_c64 ? 8 : 4;
+    if ((rc = ensure_input(ctx, n_in * isz))) return rc;
+    const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
+    if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
+    const int prev_bit = (lead != 0) ? (0.0f >= threshold) : (ctx->prev_in0 >= threshold);
+    const long long eob_in = ctx->prev_eob;
+    cudaStream_t s = ctx->stream;
+    if ((rc = begin_call(ctx, s))) return rc;
+    ScanParams P = make_params(ctx, ctx->d_in, n_in, lead, n_out, 0, threshold, base, prev_bit, 1);
+
+    // H2D in chunks on the copy stream; tiles are launched as soon as their samples (incl. the right
+    // halo) are resident, so the scan overlaps the transfer of the following chunk.
+    const char *src = static_cast<const char *>(in);
+    char *dst = static_cast<char *>(ctx->d_in);
+    size_t copied = 0;
+    long long tiles_done = 0;
+    int ring = 0;
+    while (copied < n_in) {
+        const size_t n = (n_in - copied < kPipeChunk) ? (n_in - copied) : kPipeChunk;
+        CK(cudaMemcpyAsync(dst + copied * isz, src + copied * isz, n * isz, cudaMemcpyHostToDevice, ctx->copy_stream));
+        copied += n;
+        long long ready = (copied == n_in) ? n_tiles : ((long long)copied - ctx->rh) / ctx->T;
+        if (ready > n_tiles) ready = n_tiles;
+        if (ready > tiles_done || copied == n_in) {
+            CK(cudaEventRecord(ctx->ev[ring], ctx->copy_stream));
+            CK(cudaStreamWaitEvent(s, ctx->ev[ring], 0));
+            ring = (ring + 1) % kEvRing;
+            if (ready > tiles_done) CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)(ready - tiles_done), s));
+            tiles_done = ready;
+        }
+    }
+    if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
+    ctx->last.pending = true;
+    ctx->last.n_out = (long long)n_out;
+    ctx->last.lead = (long long)lead;
+    ctx->last.base = base;
+    ctx->last.eob_in = eob_in;
+    ctx->last.left_is_start = 1;
+    ctx->last.stream = s;
+    return adsb_burst_finish(ctx, nullptr, hits, cap, n_hits);
+}
+
+int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out, float threshold,
+                     int64_t *hit_idx, float *hit_snr, size_t cap, size_t *n_hits)
+{
+    if (!ctx || !in0 || !n_hits) return ADSB_E_INVAL;
+    *n_hits = 0;
+    int rc = check_geometry(ctx, n_in, 0, n_out, 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_input(ctx, n_in * 4))) return rc;
+    cudaStream_t s = ctx->stream;
+    const long long n_tiles = tiles_for(ctx, (long long)n_out, 0);
+    const int prev_bit = ctx->prev_in0 >= threshold;
+    const long long eob_in = ctx->prev_eob;
+    CK(cudaMemcpyAsync(ctx->d_in, in0, n_in * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = begin_call(ctx, s))) return rc;
+    ScanParams P = make_params(ctx, ctx->d_in, n_in, 0, n_out, 0, threshold, 0, prev_bit, 0);
+    CK(launch_scan(ctx, P, false, (unsigned)n_tiles, s));
+    if ((rc = launch_resolve(ctx, n_tiles, 0, eob_in, s))) return rc;
+    ctx->last.pending = true;
+    ctx->last.n_out = (long long)n_out;
+    ctx->last.lead = 0;
+    ctx->last.base = 0;
+    ctx->last.eob_in = eob_in;
+    ctx->last.left_is_start = 1;
+    ctx->last.stream = s;
+    // header + hits in one synchronisation (the first kFirstHits ride along with the header)
+    size_t tcap = n_out / (size_t)(63 * ctx->sps) + 2;
+    Rec *tmp = (Rec *)malloc(tcap * sizeof(Rec));
+    if (!tmp) return fail(ctx, ADSB_E_NOMEM, "malloc");
+    size_t n = 0;
+    rc = adsb_burst_finish(ctx, nullptr, reinterpret_cast<adsb_hit *>(tmp), tcap, &n);
+    if (rc == ADSB_OK) {
+        *n_hits = n;
+        if (n > cap || (n && (!hit_idx || !hit_snr))) {
+            rc = fail(ctx, ADSB_E_CAPACITY, "hit capacity too small");
+        } else {
+            for (size_t i = 0; i < n; i++) {
+                hit_idx[i] = tmp[i].idx;
+                hit_snr[i] = tmp[i].snr;
+            }
+        }
+    }
+    free(tmp);
+    return rc;
+}
+
+int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *sob_idx, size_t n_tags,
+                    uint8_t *bits, uint8_t *valid)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    if (n_tags == 0) return ADSB_OK;             // the common work() call: nothing tagged, nothing to do
+    if (!in0 || !sob_idx || !bits || !valid) return ADSB_E_INVAL;
+    if (n > ctx->max_items + (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "n exceeds max_items");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_input(ctx, n * 4))) return rc;
+    if (n_tags > ctx->tag_cap) {
+        cudaFree(ctx->d_sob);
+        cudaFree(ctx->d_bits);
+        cudaFree(ctx->d_valid);
+        ctx->d_sob = nullptr;
+        ctx->d_bits = ctx->d_valid = nullptr;
+        ctx->tag_cap = 0;
+        size_t want = n_tags * 2;
+        CK(cudaMalloc((void **)&ctx->d_sob, want * sizeof(long long)));
+        CK(cudaMalloc((void **)&ctx->d_bits, want * kMsgBits));
+        CK(cudaMalloc((void **)&ctx->d_valid, want));
+        ctx->tag_cap = want;
+    }
+    cudaStream_t s = ctx->stream;
+    // only the span the tags can touch needs to travel
+    long long lo = (long long)n, hi = 0;
+    for (size_t t = 0; t < n_tags; t++) {
+        long long a = sob_idx[t], b = sob_idx[t] + 112LL * ctx->sps;
+        if (a < lo) lo = a;
+        if (b > hi) hi = b;
+    }
+    if (lo < 0) lo = 0;
+    if (hi > (long long)n) hi = (long long)n;
+    if (hi > lo)
+        CK(cudaMemcpyAsync((float *)ctx->d_in + lo, in0 + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_sob, sob_idx, n_tags * sizeof(long long), cudaMemcpyHostToDevice, s));
+    unsigned blocks = (unsigned)((n_tags + kWarps - 1) / kWarps);
+    if (blocks > (unsigned)ctx->num_sms * 8u) blocks = (unsigned)ctx->num_sms * 8u;
+    demod_kernel<<<blocks, kThreads, 0, s>>>((const float *)ctx->d_in, (long long)n, ctx->d_sob, (int)n_tags, ctx->sps,
+                                             ctx->d_bits, ctx->d_valid);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(valid, ctx->d_valid, n_tags, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    // bits of straddlers stay untouched in the caller's buffer
+    bool all = true;
+    for (size_t t = 0; t < n_tags; t++) all = all && valid[t];
+    if (all) {
+        CK(cudaMemcpy(bits, ctx->d_bits, n_tags * kMsgBits, cudaMemcpyDeviceToHost));
+    } else {
+        for (size_t t = 0; t < n_tags; t++)
+            if (valid[t]) CK(cudaMemcpy(bits + t * kMsgBits, ctx->d_bits + t * kMsgBits, kMsgBits, cudaMemcpyDeviceToHost));
+    }
+    return ADSB_OK;
+}
+
+}  // extern "C"

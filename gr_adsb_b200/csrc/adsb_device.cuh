@@ -1,0 +1,256 @@
+// Device-side building blocks of the B200 ADS-B burst path (sm_100a).
+//
+// K1  scan_slice_kernel   one pass over the sample buffer: |IQ|^2, threshold bitmap, pulse runs and
+//                         centres, 16-tap preamble match, and -- for every match ("candidate") --
+//                         median-noise SNR, 112-bit PPM slice and CRC-24, all out of one shared-memory
+//                         tile.  Replaces the per-sample work of framer.py:83-159 and demod.py:87-95.
+// K2  gather / chain / compact   tiny kernels over the sparse candidate list: order it, apply the
+//                         63-symbol blanking rule of framer.py:121-123,165 and emit the accepted hits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adsb {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kLeftHalo = 128;      // samples staged left of a tile: 100 (noise window) + run look-back
+constexpr int kNoise = 100;         // framer.py:31 NUM_NOISE_SAMPLES
+constexpr int kMsgBits = 112;       // demod.py:29
+constexpr int kStage = 64;          // candidate records staged in shared memory per batch
+constexpr unsigned kFull = 0xffffffffu;
+
+// flags in Header.flags
+constexpr unsigned kFlagRise = 1u, kFlagFall = 2u, kFlagCandOverflow = 4u, kFlagHalo = 8u,
+                   kFlagHitOverflow = 16u, kFlagSpin = 32u;
+
+// == adsb_hit (include/adsb_b200.h)
+struct __align__(16) Rec {
+    long long idx;
+    float snr;
+    unsigned flags;
+    unsigned bits[4];
+};
+static_assert(sizeof(Rec) == 32, "record must stay 32 bytes");
+
+constexpr unsigned kHitDemodValid = 1u, kHitCrcOk = 2u, kHitLate = 4u;
+
+struct Header {
+    unsigned long long n_cand;       // candidates allocated by K1 (atomic)
+    unsigned long long n_hits;       // accepted hits (K2 compact)
+    unsigned long long n_demod;
+    unsigned long long n_crc;
+    long long last_pulse;            // max pulse centre, window coordinates (-1: none)
+    long long last_accept;           // max accepted centre, window coordinates (-1: none)
+    unsigned flags;
+    unsigned tile_ticket;
+    unsigned chunk_ticket_g;         // gather kernel
+    unsigned chunk_ticket_c;         // compact kernel
+    float x_last;                    // x[n_out-1]  -> framer.py:87 prev_in0
+    unsigned pad[3];
+};
+
+struct ScanParams {
+    const void *in;        // float (|IQ|^2) or float2 (IQ)
+    long long n_arr;       // items in `in`
+    long long lead;        // virtual zero items before in[0]; window index = array index + lead
+    long long n_loc;       // lead + n_arr
+    long long own_lo;      // falls owned: window index in [own_lo, own_hi)
+    long long own_hi;
+    long long base;        // added to window index in the emitted records
+    long long n_tiles_total;
+    float thr;
+    int sps;
+    int rh;                // right halo, samples (multiple of 32, >= 120*sps)
+    int left_is_start;     // window index 0 is where this work() call's window starts
+    int prev_bit;          // bitmap value at window index -1 (framer.py:83-84)
+    int do_demod;
+    int hist;              // 8*sps - 1
+    Rec *cand;
+    unsigned cand_cap;
+    uint2 *tile_tab;       // per tile: (offset into cand, count)
+    Header *hdr;
+    const unsigned *crc_tab;   // 112 words: x^(111-i) mod g
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// |IQ|^2 exactly as the oracle: fl32(fl32(re*re) + fl32(im*im)), no FMA contraction (adsb_rx.py:180)
+__device__ __forceinline__ float mag2(float2 v)
+{
+    return __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
+}
+
+template <bool C64>
+__device__ __forceinline__ float load_x(const void *in, long long j)
+{
+    if (C64)
+        return mag2(ldg_stream_f2(reinterpret_cast<const float2 *>(in) + j));
+    return ldg_stream_f1(reinterpret_cast<const float *>(in) + j);
+}
+
+// window sample i (any i): zeros outside the array / inside the virtual lead
+template <bool C64>
+__device__ __forceinline__ float window_x(const ScanParams &P, long long i)
+{
+    long long j = i - P.lead;
+    if (j < 0 || j >= P.n_arr)
+        return 0.0f;
+    return load_x<C64>(P.in, j);
+}
+
+// total order on non-NaN floats as unsigned keys
+__device__ __forceinline__ unsigned f2key(float x)
+{
+    unsigned u = __float_as_uint(x);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k)
+{
+    return __uint_as_float((k >> 31) ? (k & 0x7fffffffu) : ~k);
+}
+
+// 10*log10(xp/med) + 1.6 with the reference's float32 steps (framer.py:157-159 under NumPy >= 2)
+__device__ __forceinline__ float snr_db(float xp, float med)
+{
+    float ratio = __fdiv_rn(xp, med);
+    float l = log10f(ratio);
+    return __fadd_rn(__fmul_rn(10.0f, l), 1.6f);
+}
+
+// np.median of n <= 100 floats from a generic accessor, by one thread (slow path only)
+template <class F>
+__device__ float median_serial(F get, int n)
+{
+    if (n <= 0)
+        return __int_as_float(0x7fc00000);
+    const int k1 = (n - 1) >> 1, k2 = n >> 1;
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < n; i++) {
+        float v = get(i);
+        if (v != v)
+            return __int_as_float(0x7fc00000);
+        int less = 0, eq = 0;
+        for (int j = 0; j < n; j++) {
+            float w = get(j);
+            less += (w < v);
+            eq += (w == v);
+        }
+        if (less <= k1 && k1 < less + eq) a = v;
+        if (less <= k2 && k2 < less + eq) b = v;
+    }
+    return (n & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-wide bitonic sort of 128 keys, 4 per lane, logical position e = 4*lane + r, ascending.
+__device__ __forceinline__ void warp_sort128(unsigned (&k)[4], int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            if (j >= 4) {
+                const int lm = j >> 2;
+                const bool up = ((lane << 2) & size) == 0;
+                const bool lower = (lane & lm) == 0;
+                const bool keep_min = (lower == up);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    unsigned o = __shfl_xor_sync(kFull, k[r], lm);
+                    k[r] = keep_min ? min(k[r], o) : max(k[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    if ((r & j) == 0) {
+                        const bool up = (((lane << 2) | r) & size) == 0;
+                        unsigned lo = min(k[r], k[r | j]), hi = max(k[r], k[r | j]);
+                        k[r] = up ? lo : hi;
+                        k[r | j] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned pick4(const unsigned (&k)[4], int r)
+{
+    unsigned v = k[0];
+    v = (r == 1) ? k[1] : v;
+    v = (r == 2) ? k[2] : v;
+    v = (r == 3) ? k[3] : v;
+    return v;
+}
+
+// np.median of the n <= 100 shared-memory floats w[0..n) by one warp (all lanes get the result)
+__device__ __forceinline__ float warp_median(const float *w, int n, int lane)
+{
+    unsigned k[4];
+    bool nan = false;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int e = r * 32 + lane;
+        float v = (e < n) ? w[e] : 0.0f;
+        nan |= (e < n) && (v != v);
+        k[r] = (e < n) ? f2key(v) : 0xffffffffu;
+    }
+    if (__any_sync(kFull, nan) || n <= 0)
+        return __int_as_float(0x7fc00000);
+    warp_sort128(k, lane);
+    const int k1 = (n - 1) >> 1, k2 = n >> 1;
+    unsigned a = __shfl_sync(kFull, pick4(k, k1 & 3), k1 >> 2);
+    unsigned b = __shfl_sync(kFull, pick4(k, k2 & 3), k2 >> 2);
+    float fa = key2f(a), fb = key2f(b);
+    return (n & 1) ? fa : __fdiv_rn(__fadd_rn(fa, fb), 2.0f);
+}
+
+// message bits (ballot word: bit l = message bit 32*j + l) -> numpy.packbits byte order
+__device__ __forceinline__ unsigned pack_msb_first(unsigned w)
+{
+    return __byte_perm(__brev(w), 0, 0x0123);
+}
+
+// block-wide exclusive scan of one int per thread (kThreads threads); returns exclusive prefix,
+// total in `total`.  `scratch` = kWarps + 1 ints of shared memory.
+__device__ __forceinline__ int block_excl_scan(int v, int *scratch, int &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = (lane < kWarps) ? scratch[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < kWarps; d <<= 1) {
+            int t = __shfl_up_sync(kFull, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane < kWarps) scratch[lane] = s;
+    }
+    __syncthreads();
+    total = scratch[kWarps - 1];
+    int off = (wid ? scratch[wid - 1] : 0) + inc - v;
+    __syncthreads();
+    return off;
+}
+
+}  // namespace adsb

@@ -1,0 +1,132 @@
+/*
+ * adsb_b200.h -- C ABI of the B200-native ADS-B burst-detect + PPM-demod path.
+ *
+ * gr-adsb has no FFI of its own: its hot path is two pure-Python GNU Radio blocks.  This
+ * header is the boundary a native replacement for that path binds to; each entry point names
+ * the reference code it stands in for (paths relative to the gr-adsb tree):
+ *
+ *   adsb_framer_work      python/adsb/framer.py:72-182   framer.work()
+ *   adsb_demod_work       python/adsb/demod.py:57-136    demod.work() (the PPM slice, :82-95)
+ *   adsb_burst_work*      examples/adsb_rx.py:180-196    complex_to_mag_squared -> framer -> demod
+ *                                                        (+ the parity check of decoder.py:667-685)
+ *   adsb_reset_state / adsb_get_state / adsb_set_state
+ *                         python/adsb/framer.py:54,57    prev_in0 / prev_eob_idx carried between calls
+ *
+ * Conventions: plain pointers and sizes only; every function returns ADSB_OK (0) or a negative
+ * ADSB_E_* code and never throws; nothing is written past the capacities the caller passes.
+ * A context is owned by one block instance and is not thread safe (GNU Radio calls a block's
+ * work() from one thread).  Host entry points take HOST pointers that are only read/written
+ * during the call (GNU Radio buffers are only valid for the duration of work()).
+ * "Window coordinates" below are indices into the in0 array handed to framer.work():
+ * window index i is absolute item  nitems_written(0) - (8*sps - 1) + i  (framer.py:170).
+ */
+#ifndef ADSB_B200_H
+#define ADSB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADSB_B200_ABI_VERSION 1
+
+enum {
+    ADSB_OK = 0,
+    ADSB_E_INVAL = -1,     /* bad argument (odd sps, null pointer, sizes that do not fit max_items ...) */
+    ADSB_E_CUDA = -2,      /* a CUDA runtime call failed; adsb_last_error() has the text            */
+    ADSB_E_NOMEM = -3,     /* host or device allocation failed                                       */
+    ADSB_E_CAPACITY = -4,  /* more hits than the caller's `cap`; n_hits holds the number required      */
+    ADSB_E_NODEVICE = -5,  /* no CUDA device / not an sm_100 part                                     */
+    ADSB_E_HALO = -6,      /* a pulse run crosses the left edge of a halo'd shard (multi-GPU only)    */
+    ADSB_E_INTERNAL = -7
+};
+
+/* adsb_hit.flags */
+#define ADSB_HIT_DEMOD_VALID 0x1u /* burst lies fully inside the buffer: bits[] valid (demod.py:82)            */
+#define ADSB_HIT_CRC_OK      0x2u /* DF in {17,18,19} and PI == CRC-24(bits[0:88]) (decoder.py:667-685)         */
+#define ADSB_HIT_LATE_TAG    0x4u /* window index < 8*sps-1: tag lands on an item of the previous call (A.9) */
+
+/* One detected burst.  `bits` holds the 112 demodulated bits packed MSB first (numpy.packbits
+ * order: message bit k is bit 7-(k%8) of bits[k/8]); bits[14..15] are zero. */
+typedef struct adsb_hit {
+    int64_t idx;       /* pulse-centre index p: window coordinates + the `base` given to the call     */
+    float snr;         /* 10*log10(x[p]/median(x[p-100:p])) + 1.6 dB (framer.py:156-159); nan/inf kept */
+    uint32_t flags;    /* ADSB_HIT_*                                                                   */
+    uint8_t bits[16];
+} adsb_hit;
+
+/* Per-call counters (all in items of the call's window). */
+typedef struct adsb_counters {
+    uint64_t n_samples;     /* items scanned (n_out)                                       */
+    uint64_t n_candidates;  /* pulse centres whose 16 half-symbol taps match the preamble  */
+    uint64_t n_hits;        /* candidates surviving the 63-symbol blanking -> "burst" tags */
+    uint64_t n_demod;       /* hits with ADSB_HIT_DEMOD_VALID                              */
+    uint64_t n_crc_ok;      /* hits with ADSB_HIT_CRC_OK                                   */
+    int64_t last_pulse;     /* centre of the last complete pulse, -1 if none               */
+    uint32_t any_rise;      /* framer.py:95 guard inputs                                   */
+    uint32_t any_fall;
+} adsb_counters;
+
+typedef struct adsb_ctx adsb_ctx;
+
+const char *adsb_strerror(int code);
+int adsb_abi_version(void);
+int adsb_device_count(void);
+
+/* Create a context on CUDA device `device` for `sps` samples per symbol (fs / 1e6; even, 2..32)
+ * able to take up to `max_items` input items per call.  Device buffers are sized once here. */
+int adsb_create(adsb_ctx **ctx, int device, int sps, size_t max_items);
+void adsb_destroy(adsb_ctx *ctx);
+const char *adsb_last_error(const adsb_ctx *ctx);
+
+/* framer.py:54,57 -- the state carried between work() calls. reset: prev_in0 = 0, prev_eob_idx = -1 */
+int adsb_reset_state(adsb_ctx *ctx);
+int adsb_get_state(const adsb_ctx *ctx, float *prev_in0, int64_t *prev_eob_idx);
+int adsb_set_state(adsb_ctx *ctx, float prev_in0, int64_t prev_eob_idx);
+int adsb_get_counters(const adsb_ctx *ctx, adsb_counters *out);
+
+/* framer.work(): in0[n_in] is float32 |IQ|^2 with n_in == n_out + 8*sps - 1 (GNU Radio history).
+ * Writes the pulse-centre window index and SNR of every "burst" tag, ascending; the caller adds
+ * nitems_written(0) - (8*sps-1) to get the tag offset (framer.py:168-174) and copies
+ * in0[8*sps-1:] to out0 (framer.py:181).  Updates the carried state exactly as the reference
+ * does (including the stale prev_eob_idx behaviour). */
+int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out, float threshold,
+                     int64_t *hit_idx, float *hit_snr, size_t cap, size_t *n_hits);
+
+/* demod.work() slicing: for each tag t, sob_idx[t] = tag.offset + 8*sps - nitems_written(0)
+ * (demod.py:75,79).  valid[t] = 1 and bits[t*112 .. t*112+111] (one bit per byte) are written
+ * when the burst ends inside in0[0:n] (demod.py:82); otherwise valid[t] = 0 (straddler,
+ * demod.py:130-133) and its bits are left untouched.  Stateless. */
+int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *sob_idx, size_t n_tags,
+                    uint8_t *bits, uint8_t *valid);
+
+/* Fused path over a HOST buffer: optional |IQ|^2 (is_c64: in = interleaved re,im float32 pairs,
+ * n_in complex items; else float32 |IQ|^2), framer, demod and parity check in one pass on the
+ * GPU.  The window is `lead` zero items followed by in[0:n_in]; n_out + 8*sps - 1 == lead + n_in.
+ * lead = 8*sps-1 with a freshly reset context reproduces a flowgraph's first work() call over
+ * the whole buffer ("whole-buffer mode"); lead = 0 continues a stream whose history the caller
+ * prepends, exactly like adsb_framer_work.  hits[i].idx = base + window index. */
+int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size_t lead, size_t n_out,
+                    float threshold, int64_t base, adsb_hit *hits, size_t cap, size_t *n_hits);
+
+/* Same, for a buffer already resident in device memory; runs asynchronously on CUDA stream
+ * `stream` (a cudaStream_t, may be NULL = the context's own stream) and leaves the results on the
+ * device: *d_hits is a device pointer to adsb_hit[] owned by the context (valid until the next
+ * call); counts come back through adsb_burst_finish.  `eob_in` is the incoming prev_eob_idx in
+ * window coordinates (-1 at stream start).  `halo_left` > 0 says the first `halo_left` items of d_in
+ * are a left halo copied from the neighbouring shard: pulses are owned from window index halo_left
+ * on, the window start is not the stream start, and the carried state is left alone (multi-GPU). */
+int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in, size_t lead, size_t n_out,
+                        size_t halo_left, float threshold, int64_t base, int64_t eob_in, void *stream,
+                        const adsb_hit **d_hits);
+
+/* After adsb_burst_work_dev + stream sync: fetch counters, advance the carried state as
+ * framer.py:121-123,165,177-179 would, optionally copy the hits to the host. */
+int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADSB_B200_H */
