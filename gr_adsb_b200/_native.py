@@ -26,6 +26,7 @@ assert HIT_DTYPE.itemsize == 32
 class Counters(C.Structure):
     _fields_ = [("n_samples", C.c_uint64), ("n_candidates", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_demod", C.c_uint64), ("n_crc_ok", C.c_uint64), ("last_pulse", C.c_int64),
+                ("last_accept", C.c_int64), ("first_candidate", C.c_int64),
                 ("any_rise", C.c_uint32), ("any_fall", C.c_uint32)]
 
     def as_dict(self):
@@ -53,7 +54,8 @@ _lib = None
 
 EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_create", "adsb_destroy",
            "adsb_last_error", "adsb_reset_state", "adsb_get_state", "adsb_set_state", "adsb_get_counters",
-           "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish"]
+           "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish",
+           "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev"]
 
 
 def lib():
@@ -92,6 +94,12 @@ def lib():
     L.adsb_burst_work_dev.argtypes = [vp, vp, i32, sz, sz, sz, sz, f32, i64, i64, vp, C.POINTER(vp)]
     L.adsb_burst_finish.restype = i32
     L.adsb_burst_finish.argtypes = [vp, C.POINTER(Counters), vp, sz, C.POINTER(sz)]
+    L.adsb_burst_reresolve_dev.restype = i32
+    L.adsb_burst_reresolve_dev.argtypes = [vp, i64, vp]
+    L.adsb_profile_enable.restype = i32
+    L.adsb_profile_enable.argtypes = [vp, i32]
+    L.adsb_profile_last.restype = i32
+    L.adsb_profile_last.argtypes = [vp, C.POINTER(f32), C.POINTER(f32)]
     _lib = L
     return L
 
@@ -224,6 +232,24 @@ class Context(object):
                 raise AdsbError(rc, "burst_finish: pass cap >= %d" % n.value)
             self._check(rc)
             return c.as_dict(), hits[:n.value]
+
+
+def _profile_methods():
+    def profile_enable(self, on=True):
+        self._check(lib().adsb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_last(self):
+        a, b = C.c_float(), C.c_float()
+        self._check(lib().adsb_profile_last(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+    def burst_reresolve_dev(self, eob_in, stream=0):
+        self._check(lib().adsb_burst_reresolve_dev(self._h, int(eob_in), C.c_void_p(stream)))
+    Context.burst_reresolve_dev = burst_reresolve_dev
+    Context.profile_enable = profile_enable
+    Context.profile_last = profile_last
+
+
+_profile_methods()
 
 
 def unpack_bits(hits):

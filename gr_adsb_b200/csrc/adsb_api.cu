@@ -27,6 +27,7 @@ __global__ void init_header_kernel(Header *h)
     memset(h, 0, sizeof(Header));
     h->last_pulse = -1;
     h->last_accept = -1;
+    h->first_cand = -1;
 }
 
 struct HostStage {
@@ -67,6 +68,9 @@ struct adsb_ctx {
         cudaStream_t stream;
     } last;
     adsb_counters counters;
+    int profile;
+    unsigned rerun_count;
+    cudaEvent_t pev[3];
     char err[256];
 };
 
@@ -100,30 +104,30 @@ void crc_table(unsigned *t)
     }
 }
 
-template <int T, int HS, bool C64>
+template <int SPS, bool C64>
 cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s)
 {
-    const size_t smem = tile_smem_bytes(T, P.rh);
-    static bool configured = false;   // per instantiation; one device per process in practice
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<T, HS, C64>,
+    const size_t smem = tile_smem_bytes(Geo<SPS>::T, P.rh);
+    static size_t configured = 0;   // per instantiation; one device per process in practice
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, C64>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured = smem;
     }
-    scan_slice_kernel<T, HS, C64><<<n_blocks, kThreads, smem, s>>>(P);
+    scan_slice_kernel<SPS, C64><<<n_blocks, kThreads, smem, s>>>(P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P, bool c64, unsigned n_blocks, cudaStream_t s)
 {
     if (n_blocks == 0) return cudaSuccess;
-    if (c->T == 4096) {
-        if (c->sps == 2) return c64 ? launch_scan_t<4096, 1, true>(P, n_blocks, s) : launch_scan_t<4096, 1, false>(P, n_blocks, s);
-        return c64 ? launch_scan_t<4096, 0, true>(P, n_blocks, s) : launch_scan_t<4096, 0, false>(P, n_blocks, s);
+    switch (c->sps) {
+    case 2: return c64 ? launch_scan_t<2, true>(P, n_blocks, s) : launch_scan_t<2, false>(P, n_blocks, s);
+    case 4: return c64 ? launch_scan_t<4, true>(P, n_blocks, s) : launch_scan_t<4, false>(P, n_blocks, s);
+    case 8: return c64 ? launch_scan_t<8, true>(P, n_blocks, s) : launch_scan_t<8, false>(P, n_blocks, s);
+    default: return c64 ? launch_scan_t<0, true>(P, n_blocks, s) : launch_scan_t<0, false>(P, n_blocks, s);
     }
-    if (c->sps == 8) return c64 ? launch_scan_t<8192, 4, true>(P, n_blocks, s) : launch_scan_t<8192, 4, false>(P, n_blocks, s);
-    return c64 ? launch_scan_t<8192, 0, true>(P, n_blocks, s) : launch_scan_t<8192, 0, false>(P, n_blocks, s);
 }
 
 long long tiles_for(const adsb_ctx *c, long long n_out, long long lead)
@@ -133,10 +137,11 @@ long long tiles_for(const adsb_ctx *c, long long n_out, long long lead)
 }
 
 // Validate the geometry shared by every fused entry point.
-int check_geometry(adsb_ctx *ctx, size_t n_in, size_t lead, size_t n_out, size_t halo_left)
+int check_geometry(adsb_ctx *ctx, size_t n_in, size_t lead, size_t n_out, size_t halo_left, bool shard = false)
 {
     if (n_out == 0 || n_in == 0) return fail(ctx, ADSB_E_INVAL, "empty call");
-    if (lead + n_in != n_out + (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "lead + n_in must equal n_out + 8*sps - 1");
+    if (shard ? (lead + n_in < n_out + (size_t)ctx->hist) : (lead + n_in != n_out + (size_t)ctx->hist))
+        return fail(ctx, ADSB_E_INVAL, "lead + n_in must equal n_out + 8*sps - 1");
     if (n_in > ctx->max_items) return fail(ctx, ADSB_E_INVAL, "n_in exceeds max_items given to adsb_create");
     if (lead != 0 && lead != (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "lead must be 0 or 8*sps - 1");
     if (halo_left != 0 && (halo_left < 256 || lead != 0)) return fail(ctx, ADSB_E_INVAL, "halo_left must be 0 or >= 256 with lead 0");
@@ -171,7 +176,7 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     return P;
 }
 
-int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long eob_in, cudaStream_t s)
+int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long eob_in, cudaStream_t s, bool rerun = false)
 {
     ResolveParams R;
     memset(&R, 0, sizeof(R));
@@ -193,21 +198,32 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     const long long gchunks = (n_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
     const unsigned cap_blocks = (unsigned)ctx->num_sms * 4u;
     unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
-    gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
+    if (rerun)
+        reset_resolve_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
+    else
+        gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
     chain_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
     compact_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
     CK(cudaGetLastError());
     return ADSB_OK;
 }
 
-int begin_call(adsb_ctx *ctx, cudaStream_t s)
+int bump_epoch(adsb_ctx *ctx, cudaStream_t s)
 {
+    // look-back status words carry the epoch, so nothing has to be cleared between calls
     ctx->epoch = (ctx->epoch + 1) & 0x3fffffffu;
     if (ctx->epoch == 0) {   // wrapped: stale status words could alias, clear them
         CK(cudaMemsetAsync(ctx->d_status_g, 0, ctx->status_g_n * 8, s));
         CK(cudaMemsetAsync(ctx->d_status_c, 0, ctx->status_c_n * 8, s));
         ctx->epoch = 1;
     }
+    return ADSB_OK;
+}
+
+int begin_call(adsb_ctx *ctx, cudaStream_t s)
+{
+    int rc = bump_epoch(ctx, s);
+    if (rc) return rc;
     init_header_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
     CK(cudaGetLastError());
     return ADSB_OK;
@@ -300,6 +316,8 @@ void adsb_destroy(adsb_ctx *ctx)
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < kEvRing; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 3; i++)
+        if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -322,8 +340,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->device = device;
     ctx->sps = sps;
     ctx->hist = 8 * sps - 1;
-    ctx->T = (sps <= 4) ? 4096 : 8192;
-    ctx->rh = ((120 * sps + 31) / 32) * 32;
+    ctx->T = tile_items(sps);
+    ctx->rh = right_halo(sps);
     ctx->max_items = max_items;
     ctx->prev_in0 = 0.0f;
     ctx->prev_eob = -1;
@@ -342,6 +360,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return die(ADSB_E_CUDA, "stream", e);
     for (int i = 0; i < kEvRing; i++)
         if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return die(ADSB_E_CUDA, "event", e);
+    for (int i = 0; i < 3; i++)
+        if ((e = cudaEventCreate(&ctx->pev[i])) != cudaSuccess) return die(ADSB_E_CUDA, "event", e);
 
     // candidates: at most one per 2 samples in theory, ~1 per 600 on busy air; size for 1 per 16.
     size_t cap = max_items / 16 + 4096;
@@ -407,12 +427,31 @@ int adsb_get_counters(const adsb_ctx *ctx, adsb_counters *out)
     return ADSB_OK;
 }
 
+int adsb_profile_enable(adsb_ctx *ctx, int on)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    ctx->profile = on ? 1 : 0;
+    return ADSB_OK;
+}
+
+int adsb_profile_last(adsb_ctx *ctx, float *scan_ms, float *resolve_ms)
+{
+    if (!ctx || !ctx->profile) return ADSB_E_INVAL;
+    CK(cudaEventSynchronize(ctx->pev[2]));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, ctx->pev[0], ctx->pev[1]));
+    CK(cudaEventElapsedTime(&b, ctx->pev[1], ctx->pev[2]));
+    if (scan_ms) *scan_ms = a;
+    if (resolve_ms) *resolve_ms = b;
+    return ADSB_OK;
+}
+
 int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in, size_t lead, size_t n_out,
                         size_t halo_left, float threshold, int64_t base, int64_t eob_in, void *stream,
                         const adsb_hit **d_hits)
 {
     if (!ctx || !d_in) return ADSB_E_INVAL;
-    int rc = check_geometry(ctx, n_in, lead, n_out, halo_left);
+    int rc = check_geometry(ctx, n_in, lead, n_out, halo_left, true);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
@@ -421,8 +460,11 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
     if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
     if ((rc = begin_call(ctx, s))) return rc;
     ScanParams P = make_params(ctx, d_in, n_in, lead, n_out, halo_left, threshold, base, prev_bit, 1);
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], s));
     CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)n_tiles, s));
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], s));
     if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], s));
     ctx->last.pending = true;
     ctx->last.n_out = (long long)n_out;
     ctx->last.lead = (long long)lead;
@@ -431,6 +473,22 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
     ctx->last.left_is_start = halo_left == 0;
     ctx->last.stream = s;
     if (d_hits) *d_hits = reinterpret_cast<const adsb_hit *>(ctx->d_hits);
+    return ADSB_OK;
+}
+
+int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream)
+{
+    if (!ctx || !ctx->last.pending) return ADSB_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
+    const long long n_tiles = tiles_for(ctx, ctx->last.n_out, ctx->last.lead);
+    ctx->rerun_count++;
+    int rc = bump_epoch(ctx, s);
+    if (rc) return rc;
+    rc = launch_resolve(ctx, n_tiles, ctx->last.base, eob_in, s, true);
+    if (rc) return rc;
+    ctx->last.eob_in = eob_in;
+    ctx->last.stream = s;
     return ADSB_OK;
 }
 
@@ -443,10 +501,12 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
     if (hits && cap)
         CK(cudaMemcpyAsync(ctx->h_stage->first, ctx->d_hits, sizeof(Rec) * kFirstHits, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    ctx->last.pending = false;
     const Header &h = ctx->h_stage->hdr;
     int rc = status_of(ctx, h);
-    if (rc) return rc;
+    if (rc) {
+        ctx->last.pending = false;
+        return rc;
+    }
     adsb_counters &c = ctx->counters;
     c.n_samples = (uint64_t)ctx->last.n_out;
     c.n_candidates = h.n_cand;
@@ -454,6 +514,8 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
     c.n_demod = h.n_demod;
     c.n_crc_ok = h.n_crc;
     c.last_pulse = h.last_pulse;
+    c.last_accept = h.last_accept;
+    c.first_candidate = h.first_cand;
     c.any_rise = (h.flags & kFlagRise) ? 1u : 0u;
     c.any_fall = (h.flags & kFlagFall) ? 1u : 0u;
     if (counters) *counters = c;

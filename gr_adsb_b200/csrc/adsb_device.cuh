@@ -47,7 +47,8 @@ struct Header {
     unsigned chunk_ticket_g;         // gather kernel
     unsigned chunk_ticket_c;         // compact kernel
     float x_last;                    // x[n_out-1]  -> framer.py:87 prev_in0
-    unsigned pad[3];
+    unsigned pad;
+    long long first_cand;            // first candidate centre, window coordinates (-1: none)
 };
 
 struct ScanParams {
@@ -122,36 +123,12 @@ __device__ __forceinline__ float key2f(unsigned k)
     return __uint_as_float((k >> 31) ? (k & 0x7fffffffu) : ~k);
 }
 
-// 10*log10(xp/med) + 1.6 with the reference's float32 steps (framer.py:157-159 under NumPy >= 2)
-__device__ __forceinline__ float snr_db(float xp, float med)
+// 10*log10(ratio) + 1.6 with the reference's float32 steps (framer.py:157-159 under NumPy >= 2);
+// ratio = fl32(x[p] / median)
+__device__ __forceinline__ float snr_db_from_ratio(float ratio)
 {
-    float ratio = __fdiv_rn(xp, med);
     float l = log10f(ratio);
     return __fadd_rn(__fmul_rn(10.0f, l), 1.6f);
-}
-
-// np.median of n <= 100 floats from a generic accessor, by one thread (slow path only)
-template <class F>
-__device__ float median_serial(F get, int n)
-{
-    if (n <= 0)
-        return __int_as_float(0x7fc00000);
-    const int k1 = (n - 1) >> 1, k2 = n >> 1;
-    float a = 0.f, b = 0.f;
-    for (int i = 0; i < n; i++) {
-        float v = get(i);
-        if (v != v)
-            return __int_as_float(0x7fc00000);
-        int less = 0, eq = 0;
-        for (int j = 0; j < n; j++) {
-            float w = get(j);
-            less += (w < v);
-            eq += (w == v);
-        }
-        if (less <= k1 && k1 < less + eq) a = v;
-        if (less <= k2 && k2 < less + eq) b = v;
-    }
-    return (n & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -196,17 +173,16 @@ __device__ __forceinline__ unsigned pick4(const unsigned (&k)[4], int r)
     return v;
 }
 
-// np.median of the n <= 100 shared-memory floats w[0..n) by one warp (all lanes get the result)
-__device__ __forceinline__ float warp_median(const float *w, int n, int lane)
+// np.median of n <= 100 floats held 4 per lane (any order; slots >= n ignored); all lanes get the result
+__device__ __forceinline__ float warp_median_regs(const float (&v)[4], int n, int lane)
 {
     unsigned k[4];
     bool nan = false;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        int e = r * 32 + lane;
-        float v = (e < n) ? w[e] : 0.0f;
-        nan |= (e < n) && (v != v);
-        k[r] = (e < n) ? f2key(v) : 0xffffffffu;
+        const int e = r * 32 + lane;
+        nan |= (e < n) && (v[r] != v[r]);
+        k[r] = (e < n) ? f2key(v[r]) : 0xffffffffu;
     }
     if (__any_sync(kFull, nan) || n <= 0)
         return __int_as_float(0x7fc00000);

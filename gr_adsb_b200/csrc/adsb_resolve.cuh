@@ -143,10 +143,17 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const ResolveParams P)
     const long long M = (long long)(m64 < P.cand_cap ? m64 : P.cand_cap);
     const long long e_in = P.base + P.eob_in;
     const long long D = P.blank;
+    // every record's accepted bit is assigned exactly once per launch (by the record's own thread when
+    // it is ineligible, otherwise by the head of its segment), so the kernel can be re-run with
+    // another eob_in (multi-GPU carry fix-up)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M;
          i += (long long)gridDim.x * blockDim.x) {
         const long long c = P.ord[i].idx;
-        if (c <= e_in) continue;                    // never accepted, flag stays clear
+        if (i == 0) P.hdr->first_cand = c - P.base;
+        if (c <= e_in) {                            // framer.py:121: still blanked by the incoming state
+            P.ord[i].flags &= ~kAccepted;
+            continue;
+        }
         bool head = (i == 0);
         if (!head) {
             const long long cp = P.ord[i - 1].idx;
@@ -162,9 +169,21 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const ResolveParams P)
             if (cj > last + D) {                    // framer.py:121 with prev_eob_idx = last + 63*sps
                 P.ord[j].flags |= kAccepted;
                 last = cj;
+            } else {
+                P.ord[j].flags &= ~kAccepted;
             }
         }
     }
+}
+
+// reset what compact_kernel accumulates, before a re-run of chain + compact
+__global__ void reset_resolve_kernel(Header *h)
+{
+    h->n_hits = 0;
+    h->n_demod = 0;
+    h->n_crc = 0;
+    h->last_accept = -1;
+    h->chunk_ticket_c = 0;
 }
 
 // ---- compact: accepted candidates -> ordered hit list ------------------------------------------------
@@ -216,6 +235,7 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
             const unsigned dst = s_excl + (unsigned)off;
             if (dst < P.hit_cap) {
                 r.flags &= ~kAccepted;
+                r.snr = snr_db_from_ratio(r.snr);       // K1 left x[p]/median here
                 uint4 *b = reinterpret_cast<uint4 *>(P.hits + dst);
                 b[0] = reinterpret_cast<const uint4 *>(&r)[0];
                 b[1] = reinterpret_cast<const uint4 *>(&r)[1];

@@ -1,15 +1,97 @@
 // K1: fused |IQ|^2 + threshold/run/centre + preamble match + (per match) SNR, PPM slice, CRC-24.
-// One CTA per tile of T samples; the tile plus a 128-sample left halo and a 120-symbol right halo
+// One CTA per tile of T samples; the tile plus a 128-sample left halo and a >= 120-symbol right halo
 // is staged once in shared memory as float32 |IQ|^2, so every sample is fetched from HBM once.
+//
+//   phase 1  HBM -> registers -> |IQ|^2 -> shared memory, threshold bitmap by warp ballot
+//   phase 2  bitmap -> falling edges -> pulse centres (bit-parallel for runs <= LMAX samples),
+//            dense 3-tap pre-filter, full 16-tap preamble test on the survivors
+//   phase 3  one warp per candidate: exact median of the 100-sample noise window (register bitonic
+//            sort), 112 PPM decisions by ballot, CRC-24 by XOR-reduction
+// Interior tiles of the specialised sample rates (2, 4, 8 samples/symbol) take the fast paths; tiles
+// touching the window edges, and other rates, take a generic per-edge path with identical results.
 #pragma once
 #include "adsb_device.cuh"
 
 namespace adsb {
 
+// ---- compile-time geometry per samples-per-symbol ------------------------------------------------------
+template <int SPS>
+struct Geo {
+    static constexpr int T = (SPS == 2 || SPS == 4) ? 4096 : 8192;
+    static constexpr int H = SPS / 2;                                  // 0: run-time
+    // right halo: >= 120*SPS and such that the staged span is a multiple of kThreads
+    static constexpr int RH = SPS == 2 ? 384 : SPS == 4 ? 640 : SPS == 8 ? 1152 : 0;
+    static constexpr int S = kLeftHalo + T + RH;
+    static constexpr int NPT = S / kThreads;                           // slots per thread in phase 1
+    static constexpr int LMAX = SPS == 2 ? 4 : 8;                      // run lengths resolved bit-parallel
+    static constexpr int DB = LMAX / 2;                                // how far a centre lies before its chunk
+    static constexpr int NV = (14 + 5 * H + 4 + 1 + 3) / 4;            // float4 loads of the dense pre-filter
+    static_assert(SPS == 0 || (S % kThreads == 0 && RH >= 120 * SPS), "tile geometry");
+};
+
+__host__ __device__ inline int tile_items(int sps) { return (sps == 2 || sps == 4) ? 4096 : 8192; }
+__host__ __device__ inline int right_halo(int sps)
+{
+    return sps == 2 ? 384 : sps == 4 ? 640 : sps == 8 ? 1152 : ((120 * sps + 31) / 32) * 32;
+}
+
+constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
+
+// ---- shared-memory layout ------------------------------------------------------------------------
+struct TileSmem {
+    float *mag;             // S
+    unsigned *bits;         // S/32
+    unsigned short *list;   // T/2 + 2
+    unsigned short *xmask;  // T/16   extra candidate bits (by fall position) from the long-run pass
+    unsigned short *xlong;  // T/16   which of them are long-run entries
+    unsigned short *slow;   // kSlowCap fall slots
+    Rec *stage;             // kStage
+    int *scratch;           // 16 ints
+};
+
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t tile_smem_bytes(int T, int rh)
+{
+    size_t S = (size_t)kLeftHalo + T + rh;
+    size_t b = S * 4;
+    b += align16((S / 32) * 4);
+    b += align16(((size_t)T / 2 + 2) * 2);
+    b += align16((size_t)(T / 16) * 2) * 2;
+    b += align16((size_t)kSlowCap * 2);
+    b += (size_t)kStage * sizeof(Rec);
+    b += 16 * 4;
+    return b;
+}
+
+__device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
+{
+    TileSmem s;
+    const size_t S = (size_t)kLeftHalo + T + rh;
+    s.mag = reinterpret_cast<float *>(raw);
+    raw += S * 4;
+    s.bits = reinterpret_cast<unsigned *>(raw);
+    raw += align16((S / 32) * 4);
+    s.list = reinterpret_cast<unsigned short *>(raw);
+    raw += align16(((size_t)T / 2 + 2) * 2);
+    s.xmask = reinterpret_cast<unsigned short *>(raw);
+    raw += align16((size_t)(T / 16) * 2);
+    s.xlong = reinterpret_cast<unsigned short *>(raw);
+    raw += align16((size_t)(T / 16) * 2);
+    s.slow = reinterpret_cast<unsigned short *>(raw);
+    raw += align16((size_t)kSlowCap * 2);
+    s.stage = reinterpret_cast<Rec *>(raw);
+    raw += (size_t)kStage * sizeof(Rec);
+    s.scratch = reinterpret_cast<int *>(raw);
+    return s;
+}
+
+// scratch slots
+enum { kScrTile = 12, kScrOff = 13, kScrSlowN = 14 };
+
+// ---- preamble test -----------------------------------------------------------------------------------
 // framer.py:137-147 -- taps x[p + k*h], k = 0..15, against half the centre amplitude; template
-// [1,0,1,0,0,0,0,1,0,1,0,0,0,0,0,0] (framer.py:50).  Tests are ordered so that pulses inside a
-// burst's data block are rejected after ~2 loads (two consecutive half symbols of one PPM symbol
-// cannot both be low).
+// [1,0,1,0,0,0,0,1,0,1,0,0,0,0,0,0] (framer.py:50).
 template <int HS>
 __device__ __forceinline__ bool preamble_match(const float *m, int h_rt)
 {
@@ -31,41 +113,6 @@ __device__ __forceinline__ bool preamble_match(const float *m, int h_rt)
     return xp > half;
 }
 
-// ---- slow path: a pulse whose run is too long for the shared-memory bitmap (>= 32 samples) ------
-template <bool C64>
-__device__ bool slow_centre(const ScanParams &P, long long i_f, long long &p)
-{
-    long long i = i_f - 1;
-    while (i >= 0 && window_x<C64>(P, i) >= P.thr) --i;
-    long long r;
-    if (i < 0) {
-        if (!P.left_is_start) {
-            atomicOr(&P.hdr->flags, kFlagHalo);
-            return false;
-        }
-        if (P.prev_bit) return false;           // run began before this window: no rise here (framer.py:98-100)
-        r = 0;
-    } else {
-        r = i + 1;
-    }
-    p = (r + i_f) >> 1;                          // framer.py:113
-    return true;
-}
-
-template <bool C64>
-__device__ bool slow_match(const ScanParams &P, long long p)
-{
-    const int h = P.sps >> 1;
-    const float xp = window_x<C64>(P, p);
-    const float half = __fmul_rn(xp, 0.5f);
-    const unsigned tmpl = 0x0285u;               // bits 0,2,7,9
-    for (int k = 0; k < 16; k++) {
-        bool hi = window_x<C64>(P, p + (long long)k * h) > half;
-        if (hi != (((tmpl >> k) & 1u) != 0)) return false;
-    }
-    return true;
-}
-
 __device__ __forceinline__ bool demod_in_range(const ScanParams &P, long long p)
 {
     // demod.py:67,82 in window coordinates: tag not late, last sample p + 119*sps + sps/2 inside in0
@@ -73,206 +120,387 @@ __device__ __forceinline__ bool demod_in_range(const ScanParams &P, long long p)
     return (!P.left_is_start || p >= P.hist) && last <= P.n_loc - 1;
 }
 
+// window sample i through shared memory when staged, global memory otherwise
 template <bool C64>
-__device__ void slow_slice(const ScanParams &P, long long p, Rec &rec)
-{
-    const int sps = P.sps, h = sps >> 1;
-    const float xp = window_x<C64>(P, p);
-    long long lo = p - kNoise;
-    if (lo < 0) lo = 0;
-    const int n = (int)(p - lo);
-    float med = median_serial([&](int i) { return window_x<C64>(P, lo + i); }, n);
-    rec.idx = P.base + p;
-    rec.snr = snr_db(xp, med);
-    unsigned flags = (P.left_is_start && p < P.hist) ? kHitLate : 0u;
-    unsigned w[4] = {0, 0, 0, 0};
-    if (P.do_demod && demod_in_range(P, p)) {
-        flags |= kHitDemodValid;
-        unsigned syn = 0;
-        for (int b = 0; b < kMsgBits; b++) {
-            long long s = p + 8LL * sps + (long long)b * sps;
-            if (window_x<C64>(P, s) > window_x<C64>(P, s + h)) {
-                w[b >> 5] |= 1u << (b & 31);
-                syn ^= P.crc_tab[b];
-            }
-        }
-        const unsigned df = __brev(w[0]) >> 27;
-        if (syn == 0 && df >= 17 && df <= 19) flags |= kHitCrcOk;
+struct Access {
+    const ScanParams &P;
+    const float *mag;
+    long long w0;
+    int S;
+    __device__ __forceinline__ float operator()(long long i) const
+    {
+        const long long s = i - w0;
+        if (s >= 0 && s < S) return mag[s];
+        return window_x<C64>(P, i);
     }
-    rec.flags = flags;
-#pragma unroll
-    for (int j = 0; j < 4; j++) rec.bits[j] = pack_msb_first(w[j]);
-}
-
-// ---- shared-memory layout ------------------------------------------------------------------------
-struct TileSmem {
-    float *mag;             // S
-    unsigned *bits;         // S/32
-    unsigned short *list;   // T/2 + 2
-    Rec *stage;             // kStage
-    int *scratch;           // 16 ints
 };
 
-__host__ __device__ inline size_t tile_smem_bytes(int T, int rh)
+// ---- long runs: warp-cooperative walk back to the rising edge ------------------------------------------
+// Fall at shared-memory slot kf (window index w0 + kf).  Returns false when the pulse has no rising edge
+// inside this window (framer.py:98-100).  All 32 lanes participate and get the same answer.
+template <bool C64>
+__device__ bool resolve_long(const ScanParams &P, const TileSmem &sm, long long w0, int kf, int lane, long long &p)
 {
-    size_t S = (size_t)kLeftHalo + T + rh;
-    size_t b = S * 4;                    // mag
-    b += ((S / 32) * 4 + 15) & ~(size_t)15;  // bits
-    b += (((size_t)T / 2 + 2) * 2 + 15) & ~(size_t)15;   // list
-    b += (size_t)kStage * sizeof(Rec);
-    b += 16 * 4;
-    return b;
+    // 1) bitmap in shared memory, 32 words per step
+    int top = kf - 1;                       // highest slot that is part of the run
+    long long r = -(1LL << 62);
+    bool found = false;
+    for (int wbase = top >> 5; wbase >= 0 && !found; wbase -= 32) {
+        const int wi = wbase - lane;
+        unsigned z = 0;
+        if (wi >= 0) {
+            z = ~sm.bits[wi];
+            if (wi == (top >> 5) && (top & 31) != 31) z &= (2u << (top & 31)) - 1u;
+        }
+        const unsigned has = __ballot_sync(kFull, z != 0);
+        if (has) {
+            const int src = __ffs(has) - 1;
+            const unsigned zz = __shfl_sync(kFull, z, src);
+            const int wz = wbase - src;
+            r = w0 + (long long)wz * 32 + (31 - __clz(zz)) + 1;
+            found = true;
+        }
+    }
+    // 2) beyond the staged span: global memory, 32 samples per step
+    if (!found) {
+        long long i0 = w0 - 1;              // next window index to examine
+        while (true) {
+            const long long i = i0 - lane;
+            bool below;
+            if (i >= 0) below = !(window_x<C64>(P, i) >= P.thr);
+            else if (i == -1) below = !(P.left_is_start && P.prev_bit);
+            else below = true;
+            const unsigned b = __ballot_sync(kFull, below);
+            if (b) {
+                r = i0 - (__ffs(b) - 1) + 1;
+                break;
+            }
+            i0 -= 32;
+        }
+    }
+    if (r < 0) {
+        // the run reaches window index -1 with the bitmap still high there
+        if (!P.left_is_start && lane == 0) atomicOr(&P.hdr->flags, kFlagHalo);
+        return false;
+    }
+    if (r == 0 && !P.left_is_start) {
+        // a halo'd shard cannot tell whether the run continues to the left of its halo
+        if (lane == 0) atomicOr(&P.hdr->flags, kFlagHalo);
+        return false;
+    }
+    p = (r + (w0 + kf)) >> 1;                // framer.py:113
+    return true;
 }
 
-template <int T>
-__device__ __forceinline__ TileSmem carve(unsigned char *raw, int rh)
+// 16-tap test by one warp through the generic accessor
+template <bool C64>
+__device__ __forceinline__ bool warp_match(const Access<C64> &X, long long p, int h, int lane)
 {
-    TileSmem s;
-    const size_t S = (size_t)kLeftHalo + T + rh;
-    s.mag = reinterpret_cast<float *>(raw);
-    raw += S * 4;
-    s.bits = reinterpret_cast<unsigned *>(raw);
-    raw += ((S / 32) * 4 + 15) & ~(size_t)15;
-    s.list = reinterpret_cast<unsigned short *>(raw);
-    raw += (((size_t)T / 2 + 2) * 2 + 15) & ~(size_t)15;
-    s.stage = reinterpret_cast<Rec *>(raw);
-    raw += (size_t)kStage * sizeof(Rec);
-    s.scratch = reinterpret_cast<int *>(raw);
-    return s;
+    const float xp = X(p);
+    const float half = __fmul_rn(xp, 0.5f);
+    bool hi = false;
+    if (lane < 16) hi = X(p + (long long)lane * h) > half;
+    return (__ballot_sync(kFull, hi) & 0xffffu) == 0x0285u;
 }
 
-// run length of ones ending just below bit `pos` (32 <= pos <= 63) of V
-__device__ __forceinline__ int ones_below(unsigned long long V, int pos)
+// ---- per-candidate slice ------------------------------------------------------------------------------
+// SNR ratio x[p] / median(noise window), 112 PPM decisions, CRC.  One warp; get(d) returns window sample p + d.
+template <class Get>
+__device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, long long p, int sps, int h, int lane,
+                                                const unsigned (&crc_t)[4], bool always_valid, Rec &rec)
 {
-    return __clzll((long long)~(V << (64 - pos)));
+    int n = kNoise;                                   // framer.py:156-159
+    if (!always_valid && p < kNoise) n = (int)p;
+    float v[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = r * 32 + lane;
+        v[r] = (e < n) ? get(e - n) : 0.0f;
+    }
+    const float med = warp_median_regs(v, n, lane);
+    const float xp = get(0);
+    unsigned flags = (!always_valid && P.left_is_start && p < P.hist) ? kHitLate : 0u;
+    unsigned w[4] = {0u, 0u, 0u, 0u};
+    if (P.do_demod && (always_valid || demod_in_range(P, p))) {
+        flags |= kHitDemodValid;
+        const int sob = 8 * sps;                          // demod.py:75
+        unsigned syn = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int bi = j * 32 + lane;
+            bool bit = false;
+            if (bi < kMsgBits) bit = get(sob + bi * sps) > get(sob + bi * sps + h);   // demod.py:87-95
+            w[j] = __ballot_sync(kFull, bit);
+            syn ^= bit ? crc_t[j] : 0u;
+        }
+        syn = __reduce_xor_sync(kFull, syn);
+        const unsigned df = __brev(w[0]) >> 27;
+        if (syn == 0 && df >= 17 && df <= 19) flags |= kHitCrcOk;    // decoder.py:667-685
+    }
+    if (lane == 0) {
+        rec.idx = P.base + p;
+        rec.snr = __fdiv_rn(xp, med);      // ratio; the compact kernel applies 10*log10(.)+1.6
+        rec.flags = flags;
+    }
+    if (lane < 4) rec.bits[lane] = pack_msb_first(lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]);
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-template <int T, int HS, bool C64>
-__global__ void __launch_bounds__(kThreads, (T <= 4096) ? 4 : 2) scan_slice_kernel(const ScanParams P)
+template <int SPS, bool C64>
+__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_slice_kernel(const ScanParams P)
 {
+    using G = Geo<SPS>;
+    constexpr int T = G::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TileSmem sm = carve<T>(smem_raw, P.rh);
+    const int rh = SPS ? G::RH : P.rh;
+    const TileSmem sm = carve(smem_raw, T, rh);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int S = kLeftHalo + T + P.rh;
-    const int h = HS ? HS : (P.sps >> 1);
+    const int S = kLeftHalo + T + rh;
+    const int h = SPS ? G::H : (P.sps >> 1);
+    const float thr = P.thr;
 
     // ---- tile id (ticket: tiles start in index order whatever the CTA dispatch order) ----
-    if (tid == 0) sm.scratch[12] = (int)atomicAdd(&P.hdr->tile_ticket, 1u);
+    if (tid == 0) {
+        sm.scratch[kScrTile] = (int)atomicAdd(&P.hdr->tile_ticket, 1u);
+        sm.scratch[kScrSlowN] = 0;
+    }
     __syncthreads();
-    const long long tile = sm.scratch[12];
+    const long long tile = sm.scratch[kScrTile];
     const long long a0 = tile * T;                 // array index of the tile's first owned sample
     const long long w0 = a0 + P.lead - kLeftHalo;  // window index of shared-memory slot 0
-    const bool interior = (a0 - kLeftHalo >= 0) && (a0 + T + P.rh <= P.n_arr) &&
+    const bool interior = (a0 - kLeftHalo >= 0) && (a0 + T + rh <= P.n_arr) &&
                           (w0 + kLeftHalo >= P.own_lo) && (w0 + kLeftHalo + T <= P.own_hi) && (w0 > 0);
+    const bool fast = SPS != 0 && interior;
 
     // ---- phase 1: HBM -> |IQ|^2 tile + threshold bitmap ----
-    {
+    if (fast) {
         constexpr int U = 6;
-        const float thr = P.thr;
-        for (int kb = wid * 32; kb < S; kb += kThreads * U) {
-            float x[U];
-            if (interior) {
-                if (C64) {
-                    const float2 *src = reinterpret_cast<const float2 *>(P.in) + (a0 - kLeftHalo) + lane;
-                    float2 v[U];
+        if (C64) {
+            const float2 *src = reinterpret_cast<const float2 *>(P.in) + (a0 - kLeftHalo) + tid;
 #pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (kb + u * kThreads < S) v[u] = ldg_stream_f2(src + kb + u * kThreads);
+            for (int u0 = 0; u0 < G::NPT; u0 += U) {
+                float2 v[U];
 #pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (kb + u * kThreads < S) x[u] = mag2(v[u]);
-                } else {
-                    const float *src = reinterpret_cast<const float *>(P.in) + (a0 - kLeftHalo) + lane;
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (kb + u * kThreads < S) x[u] = ldg_stream_f1(src + kb + u * kThreads);
-                }
+                for (int u = 0; u < U; u++)
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_f2(src + (u0 + u) * kThreads);
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const int k = kb + u * kThreads;
-                    if (k < S) {
-                        sm.mag[k + lane] = x[u];
-                        unsigned w = __ballot_sync(kFull, x[u] >= thr);
-                        if (lane == 0) sm.bits[k >> 5] = w;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int k = kb + u * kThreads;
-                    if (k < S) {
-                        const long long i = w0 + k + lane;
-                        const float v = (i >= 0 && i < P.n_loc) ? window_x<C64>(P, i) : 0.0f;
-                        bool bit = v >= thr;
-                        if (i < 0) bit = P.left_is_start ? (i == -1 && P.prev_bit) : false;
-                        sm.mag[k + lane] = v;
-                        unsigned w = __ballot_sync(kFull, bit);
-                        if (lane == 0) sm.bits[k >> 5] = w;
+                    if (u0 + u < G::NPT) {
+                        const float x = mag2(v[u]);
+                        sm.mag[(u0 + u) * kThreads + tid] = x;
+                        const unsigned w = __ballot_sync(kFull, x >= thr);
+                        if (lane == 0) sm.bits[(u0 + u) * kWarps + wid] = w;
                     }
                 }
             }
+        } else {
+            const float *src = reinterpret_cast<const float *>(P.in) + (a0 - kLeftHalo) + tid;
+#pragma unroll
+            for (int u0 = 0; u0 < G::NPT; u0 += U) {
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_f1(src + (u0 + u) * kThreads);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (u0 + u < G::NPT) {
+                        sm.mag[(u0 + u) * kThreads + tid] = v[u];
+                        const unsigned w = __ballot_sync(kFull, v[u] >= thr);
+                        if (lane == 0) sm.bits[(u0 + u) * kWarps + wid] = w;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int k = wid * 32; k < S; k += kThreads) {
+            const long long i = w0 + k + lane;
+            const float v = (i >= 0 && i < P.n_loc) ? window_x<C64>(P, i) : 0.0f;
+            bool bit = v >= thr;
+            if (i < 0) bit = P.left_is_start ? (i == -1 && P.prev_bit) : false;
+            sm.mag[k + lane] = v;
+            const unsigned w = __ballot_sync(kFull, bit);
+            if (lane == 0) sm.bits[k >> 5] = w;
         }
     }
     __syncthreads();
 
     // ---- phase 2: falls -> pulse centres -> preamble match ----
+    // Each thread owns the falls of 16-sample chunks; W holds the chunk in bits 16..31 and the 16 samples
+    // before it in bits 0..15.  cmask: candidates keyed by the bit of their FALL inside the chunk.
     constexpr int NCH = (T / 16 + kThreads - 1) / kThreads;
-    unsigned cmask[NCH], smask[NCH];
-    int tmax = -1;              // largest centre (shared-memory slot) of a complete pulse
-    long long tmax_slow = -1;   // same for slow-path pulses (window index)
+    unsigned cmask[NCH], lmask[NCH];
+    int tmax = -1;              // largest centre (shared-memory slot) of a complete short pulse
     unsigned tflags = 0;
+    bool have_long = false;
 #pragma unroll
     for (int ci = 0; ci < NCH; ci++) {
         const int c = tid + ci * kThreads;
         cmask[ci] = 0;
-        smask[ci] = 0;
+        lmask[ci] = 0;
         if (c >= T / 16) continue;
-        const int w = kLeftHalo / 32 + (c >> 1), sh = (c & 1) * 16;
-        const unsigned long long V = ((unsigned long long)sm.bits[w] << 32) | sm.bits[w - 1];
-        const unsigned long long F = ~V & (V << 1);
-        const unsigned long long R = V & ~(V << 1);
-        unsigned fm = (unsigned)(F >> (32 + sh)) & 0xffffu;
-        unsigned rm = (unsigned)(R >> (32 + sh)) & 0xffffu;
-        const int k0 = kLeftHalo + c * 16;       // slot of chunk bit 0
-        if (!interior) {
+        const int wq = kLeftHalo / 32 + (c >> 1);
+        const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
+        const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
+        unsigned F = ~W & (W << 1) & 0xffff0000u;
+        unsigned R = W & ~(W << 1) & 0xffff0000u;
+        const int k0 = kLeftHalo + c * 16;       // slot of chunk bit 0 (= W bit 16)
+        unsigned cm = 0, longf = 0;
+        if (fast) {
+            if (R) tflags |= kFlagRise;
+            if (F) tflags |= kFlagFall;
+            // bit-parallel centres: run of length L ending at fall f has centre f - ceil(L/2) (framer.py:113)
+            unsigned acc = F, C = 0;
+#pragma unroll
+            for (int L = 1; L <= G::LMAX; L++) {
+                const unsigned nxt = W << (L + 1);
+                C |= (acc & ~nxt) >> ((L + 1) >> 1);
+                acc &= nxt;
+            }
+            longf = acc >> 16;                                  // runs longer than LMAX: deferred
+            if (C) {
+                tmax = k0 + (31 - __clz(C)) - 16;
+                // dense pre-filter: taps 3,4,5 must not exceed half the centre sample (framer.py:141,50)
+                float vals[G::NV * 4];
+#pragma unroll
+                for (int q = 0; q < G::NV; q++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(sm.mag + k0 - 4 + 4 * q);
+                    vals[4 * q] = t.x; vals[4 * q + 1] = t.y; vals[4 * q + 2] = t.z; vals[4 * q + 3] = t.w;
+                }
+                unsigned Q = 0;
+#pragma unroll
+                for (int j = 0; j < 15 + G::DB; j++) {
+                    const int i0 = 4 - G::DB + j;                 // index of position k0 - DB + j in vals
+                    const float half = __fmul_rn(vals[i0], 0.5f);
+                    const bool ok = !(vals[i0 + 3 * G::H] > half) && !(vals[i0 + 4 * G::H] > half) &&
+                                    !(vals[i0 + 5 * G::H] > half);
+                    Q |= ok ? (1u << (16 - G::DB + j)) : 0u;
+                }
+                unsigned Tm = C & Q;
+                while (Tm) {
+                    const int pc = 31 - __clz(Tm);
+                    Tm &= ~(1u << pc);
+                    if (preamble_match<G::H>(sm.mag + k0 + pc - 16, h)) {
+                        // key the candidate by its fall: first zero above the centre
+                        const int fb = pc + __ffs(~(W >> (pc + 1)));
+                        cm |= 1u << (fb - 16);
+                    }
+                }
+            }
+        } else {
+            // generic per-edge path (window edges, halo'd shards, unspecialised sample rates)
             const long long i0 = w0 + k0;
             long long lo = P.own_lo - i0, hi = P.own_hi - i0;
             lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
             hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
-            const unsigned own = (hi > lo) ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
-            fm &= own;
-            rm &= own;
-        }
-        if (rm) tflags |= kFlagRise;
-        if (fm) tflags |= kFlagFall;
-        unsigned cm = 0, sl = 0;
-        while (fm) {
-            const int b = __ffs(fm) - 1;
-            fm &= fm - 1;
-            const int pos = 32 + sh + b;
-            const int run = ones_below(V, pos);
-            const int kf = k0 + b;
-            if (run >= pos) {
-                // run longer than the bitmap window: resolve from global memory
-                long long p;
-                if (slow_centre<C64>(P, w0 + kf, p)) {
-                    tmax_slow = p > tmax_slow ? p : tmax_slow;
-                    if (slow_match<C64>(P, p)) { cm |= 1u << b; sl |= 1u << b; }
+            const unsigned own = (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << 16) : 0u;
+            F &= own;
+            R &= own;
+            if (R) tflags |= kFlagRise;
+            if (F) tflags |= kFlagFall;
+            unsigned fm = F >> 16;
+            while (fm) {
+                const int b = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const int pos = 16 + b;                         // bit of the fall in W
+                const int run = __clz(~(W << (32 - pos)));      // ones just below it (pos if all of them)
+                if (run >= pos) {
+                    longf |= 1u << b;
+                    continue;
                 }
-                continue;
+                const int kf = k0 + b;
+                if (w0 + kf - run < 0) {
+                    // the run reaches window index -1: it began before this window (framer.py:98-100)
+                    if (!P.left_is_start) atomicOr(&P.hdr->flags, kFlagHalo);
+                    continue;
+                }
+                const int kp = kf - ((run + 1) >> 1);           // framer.py:113
+                tmax = kp > tmax ? kp : tmax;
+                if (preamble_match<0>(sm.mag + kp, h)) cm |= 1u << b;
             }
-            if (!interior && (w0 + kf - run) < 0) {
-                // run reaches window index -1: it began before this window (or before the halo)
-                if (!P.left_is_start) atomicOr(&P.hdr->flags, kFlagHalo);
-                continue;
+        }
+        if (longf) {
+            have_long = true;
+            unsigned lf = longf;
+            while (lf) {
+                const int b = __ffs(lf) - 1;
+                lf &= lf - 1;
+                const int slot = atomicAdd(&sm.scratch[kScrSlowN], 1);
+                if (slot < kSlowCap) sm.slow[slot] = (unsigned short)(k0 + b);
             }
-            const int kp = kf - ((run + 1) >> 1);    // framer.py:113: (rise + fall) // 2
-            tmax = kp > tmax ? kp : tmax;
-            if (preamble_match<HS>(sm.mag + kp, h)) cm |= 1u << b;
         }
         cmask[ci] = cm;
-        smask[ci] = sl;
+    }
+
+    // ---- long runs (rare): one warp per deferred fall ----
+    __shared__ long long s_max_long;
+    if (__syncthreads_or(have_long)) {
+        for (int c = tid; c < T / 16; c += kThreads) {
+            sm.xmask[c] = 0;
+            sm.xlong[c] = 0;
+        }
+        if (tid == 0) s_max_long = -1;
+        __syncthreads();
+        const int n_slow = sm.scratch[kScrSlowN];
+        const Access<C64> X{P, sm.mag, w0, S};
+        if (n_slow <= kSlowCap) {
+            for (int e = wid; e < n_slow; e += kWarps) {
+                const int kf = sm.slow[e];
+                long long p;
+                if (!resolve_long<C64>(P, sm, w0, kf, lane, p)) continue;
+                const bool m = warp_match<C64>(X, p, h, lane);
+                if (lane == 0) {
+                    atomicMax(&s_max_long, p);
+                    if (m) {
+                        const int c = (kf - kLeftHalo) >> 4, b = (kf - kLeftHalo) & 15;
+                        atomicOr(reinterpret_cast<unsigned *>(sm.xmask) + (c >> 1), (1u << b) << ((c & 1) * 16));
+                        atomicOr(reinterpret_cast<unsigned *>(sm.xlong) + (c >> 1), (1u << b) << ((c & 1) * 16));
+                    }
+                }
+            }
+        } else {
+            // more long runs than the deferral list holds: every warp rescans its own chunks
+            for (int c = wid; c < T / 16; c += kWarps) {
+                const int wq = kLeftHalo / 32 + (c >> 1);
+                const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
+                const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
+                unsigned F = ~W & (W << 1) & 0xffff0000u;
+                const int k0 = kLeftHalo + c * 16;
+                const long long i0 = w0 + k0;
+                long long lo = P.own_lo - i0, hi = P.own_hi - i0;
+                lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
+                hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
+                F &= (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << 16) : 0u;
+                unsigned fm = F >> 16;
+                while (fm) {
+                    const int b = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    const int pos = 16 + b;
+                    const int run = __clz(~(W << (32 - pos)));
+                    if (fast ? (run <= G::LMAX) : (run < pos)) continue;     // handled as a short run already
+                    long long p;
+                    if (!resolve_long<C64>(P, sm, w0, k0 + b, lane, p)) continue;
+                    const bool m = warp_match<C64>(X, p, h, lane);
+                    if (lane == 0) {
+                        atomicMax(&s_max_long, p);
+                        if (m) {
+                            atomicOr(reinterpret_cast<unsigned *>(sm.xmask) + (c >> 1), (1u << b) << ((c & 1) * 16));
+                            atomicOr(reinterpret_cast<unsigned *>(sm.xlong) + (c >> 1), (1u << b) << ((c & 1) * 16));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ci = 0; ci < NCH; ci++) {
+            const int c = tid + ci * kThreads;
+            if (c < T / 16) {
+                cmask[ci] |= sm.xmask[c];
+                lmask[ci] = sm.xlong[c];
+            }
+        }
+    } else if (tid == 0) {
+        s_max_long = -1;
     }
 
     // ---- ordered compaction of this tile's candidates into sm.list ----
@@ -286,44 +514,38 @@ __global__ void __launch_bounds__(kThreads, (T <= 4096) ? 4 : 2) scan_slice_kern
         while (cm) {
             const int b = __ffs(cm) - 1;
             cm &= cm - 1;
-            sm.list[off++] = (unsigned short)((k0 + b) | (((smask[ci] >> b) & 1u) << 15));
+            sm.list[off++] = (unsigned short)((k0 + b) | (((lmask[ci] >> b) & 1u) << 15));
         }
         n_cand += total;
     }
 
     // ---- per-tile reductions: edge flags, last pulse; candidate slot allocation ----
     {
-        __shared__ long long s_max[kWarps];
+        __shared__ int s_max[kWarps];
         __shared__ unsigned s_flag[kWarps];
         const unsigned f = __reduce_or_sync(kFull, tflags);
         const int m = __reduce_max_sync(kFull, tmax);
-        long long ms = tmax_slow;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const long long o = __shfl_xor_sync(kFull, ms, d);
-            ms = o > ms ? o : ms;
-        }
-        long long mw = (m >= 0) ? (w0 + m) : -1;
-        mw = ms > mw ? ms : mw;
         if (lane == 0) {
             s_flag[wid] = f;
-            s_max[wid] = mw;
+            s_max[wid] = m;
         }
         __syncthreads();
         if (tid == 0) {
             unsigned ff = 0;
-            long long mm = -1;
+            int mi = -1;
 #pragma unroll
             for (int q = 0; q < kWarps; q++) {
                 ff |= s_flag[q];
-                mm = s_max[q] > mm ? s_max[q] : mm;
+                mi = s_max[q] > mi ? s_max[q] : mi;
             }
+            long long mm = (mi >= 0) ? (w0 + mi) : -1;
+            mm = s_max_long > mm ? s_max_long : mm;
             if (ff) atomicOr(&P.hdr->flags, ff);
             if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
             unsigned off = 0;
             if (n_cand > 0) off = (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
             P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
-            sm.scratch[13] = (int)off;
+            sm.scratch[kScrOff] = (int)off;
             // x[n_out - 1] for the carried prev_in0 (framer.py:87)
             const long long kl = (P.own_hi - 1) - w0;
             if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
@@ -331,12 +553,13 @@ __global__ void __launch_bounds__(kThreads, (T <= 4096) ? 4 : 2) scan_slice_kern
         __syncthreads();
     }
     if (n_cand == 0) return;
-    const unsigned g_off = (unsigned)sm.scratch[13];
+    const unsigned g_off = (unsigned)sm.scratch[kScrOff];
 
-    // ---- phase 3: per-candidate SNR + PPM slice + CRC, one warp per candidate ----
+    // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC, one warp per candidate ----
     unsigned crc_t[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
+    const Access<C64> X{P, sm.mag, w0, S};
 
     for (int b0 = 0; b0 < n_cand; b0 += kStage) {
         const int nb = min(kStage, n_cand - b0);
@@ -345,47 +568,18 @@ __global__ void __launch_bounds__(kThreads, (T <= 4096) ? 4 : 2) scan_slice_kern
             const int kf = e & 0x7fff;
             Rec &rec = sm.stage[c];
             if (e >> 15) {
-                if (lane == 0) {
-                    long long p;
-                    slow_centre<C64>(P, w0 + kf, p);
-                    slow_slice<C64>(P, p, rec);
-                }
+                long long p;
+                resolve_long<C64>(P, sm, w0, kf, lane, p);
+                slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, P.sps, h, lane, crc_t, false, rec);
                 continue;
             }
+            // short run: recover the centre from the 32 bitmap bits below the fall
             const int wq = kf >> 5, bq = kf & 31;
-            const unsigned long long V = ((unsigned long long)sm.bits[wq] << 32) | sm.bits[wq - 1];
-            const int run = ones_below(V, 32 + bq);
+            const unsigned Wv = __funnelshift_r(sm.bits[wq - 1], sm.bits[wq], bq);
+            const int run = __clz(~Wv);
             const int kp = kf - ((run + 1) >> 1);
-            const long long p = w0 + kp;
-            // noise window x[max(0, p-100) : p] (framer.py:156-159)
-            int n = kNoise;
-            if (p < kNoise) n = (int)p;
-            const float med = warp_median(sm.mag + kp - n, n, lane);
-            const float xp = sm.mag[kp];
-            unsigned flags = (P.left_is_start && p < P.hist) ? kHitLate : 0u;
-            unsigned w[4] = {0u, 0u, 0u, 0u};
-            if (P.do_demod && demod_in_range(P, p)) {
-                flags |= kHitDemodValid;
-                const float *sob = sm.mag + kp + 8 * P.sps;       // demod.py:75
-                unsigned syn = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int bi = j * 32 + lane;
-                    bool bit = false;
-                    if (bi < kMsgBits) bit = sob[bi * P.sps] > sob[bi * P.sps + h];   // demod.py:87-95
-                    w[j] = __ballot_sync(kFull, bit);
-                    syn ^= bit ? crc_t[j] : 0u;
-                }
-                syn = __reduce_xor_sync(kFull, syn);
-                const unsigned df = __brev(w[0]) >> 27;
-                if (syn == 0 && df >= 17 && df <= 19) flags |= kHitCrcOk;    // decoder.py:667-685
-            }
-            if (lane == 0) {
-                rec.idx = P.base + p;
-                rec.snr = snr_db(xp, med);
-                rec.flags = flags;
-            }
-            if (lane < 4) rec.bits[lane] = pack_msb_first(lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]);
+            const float *mp = sm.mag + kp;
+            slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kp, SPS ? SPS : P.sps, h, lane, crc_t, fast, rec);
         }
         __syncthreads();
         // coalesced copy-out: 2 x 16 bytes per record

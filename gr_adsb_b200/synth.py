@@ -134,7 +134,7 @@ def mag2(iq):
 
 
 def synth_torch(n_samples, sps, n_bursts, seed, device, noise_var=1e-3, amp_db=(-10.0, 0.0),
-                start_lo=104, return_truth=True):
+                start_lo=104, return_truth=True, out=None):
     """Same construction in torch, directly on `device`; returns (iq complex64[n] as float32[n,2],
     truth dict of device tensors)."""
     import torch
@@ -142,7 +142,8 @@ def synth_torch(n_samples, sps, n_bursts, seed, device, noise_var=1e-3, amp_db=(
     g.manual_seed(int(seed))
     h = sps // 2
     blen = burst_len(sps)
-    iq = torch.empty((n_samples, 2), dtype=torch.float32, device=device)
+    iq = out if out is not None else torch.empty((n_samples, 2), dtype=torch.float32, device=device)
+    assert iq.shape == (n_samples, 2) and iq.is_contiguous()
     iq.normal_(0.0, float(np.sqrt(noise_var / 2.0)), generator=g)
     nb = int(n_bursts)
     if nb == 0:

@@ -65,6 +65,8 @@ typedef struct adsb_counters {
     uint64_t n_demod;       /* hits with ADSB_HIT_DEMOD_VALID                              */
     uint64_t n_crc_ok;      /* hits with ADSB_HIT_CRC_OK                                   */
     int64_t last_pulse;     /* centre of the last complete pulse, -1 if none               */
+    int64_t last_accept;    /* centre of the last hit, window coordinates, -1 if none       */
+    int64_t first_candidate;/* centre of the first candidate, window coordinates, -1 if none */
     uint32_t any_rise;      /* framer.py:95 guard inputs                                   */
     uint32_t any_fall;
 } adsb_counters;
@@ -113,7 +115,7 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
 
 /* Same, for a buffer already resident in device memory; runs asynchronously on CUDA stream
  * `stream` (a cudaStream_t, may be NULL = the context's own stream) and leaves the results on the
- * device: *d_hits is a device pointer to adsb_hit[] owned by the context (valid until the next
+ * device (n_out + 8*sps - 1 <= lead + n_in here: items past that are a right halo): *d_hits is a device pointer to adsb_hit[] owned by the context (valid until the next
  * call); counts come back through adsb_burst_finish.  `eob_in` is the incoming prev_eob_idx in
  * window coordinates (-1 at stream start).  `halo_left` > 0 says the first `halo_left` items of d_in
  * are a left halo copied from the neighbouring shard: pulses are owned from window index halo_left
@@ -125,6 +127,18 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
 /* After adsb_burst_work_dev + stream sync: fetch counters, advance the carried state as
  * framer.py:121-123,165,177-179 would, optionally copy the hits to the host. */
 int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits);
+
+/* Multi-GPU carry fix-up: re-apply the blanking rule to the candidates of the last
+ * adsb_burst_work_dev call with another incoming prev_eob_idx (window coordinates) -- only the two
+ * tiny resolve kernels run again.  Follow with adsb_burst_finish (which may be called repeatedly;
+ * each call re-reads the counters of the latest resolve). */
+int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream);
+
+/* Measurement hook for bench.py: when enabled, adsb_burst_work_dev records CUDA events on its launch
+ * stream before the scan kernel, after it and after the resolve kernels; adsb_profile_last waits for
+ * the last one and returns the two durations in milliseconds. */
+int adsb_profile_enable(adsb_ctx *ctx, int on);
+int adsb_profile_last(adsb_ctx *ctx, float *scan_ms, float *resolve_ms);
 
 #ifdef __cplusplus
 }
