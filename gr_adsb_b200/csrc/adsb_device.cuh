@@ -133,32 +133,54 @@ __device__ __forceinline__ float snr_db_from_ratio(float ratio)
 
 // ---------------------------------------------------------------------------------------------
 // Warp-wide bitonic sort of 128 keys, 4 per lane, logical position e = 4*lane + r, ascending.
+// "Mirrored" formulation: the first step of every merge pairs e with e ^ (size-1), the rest pair e with
+// e ^ j, and every comparator is ascending -- no direction flags, so an in-lane exchange is min + max.
+__device__ __forceinline__ void cex(unsigned &a, unsigned &b)
+{
+    const unsigned lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
 __device__ __forceinline__ void warp_sort128(unsigned (&k)[4], int lane)
 {
 #pragma unroll
     for (int size = 2; size <= 128; size <<= 1) {
+        // mirror step
+        if (size == 2) {
+            cex(k[0], k[1]);
+            cex(k[2], k[3]);
+        } else if (size == 4) {
+            cex(k[0], k[3]);
+            cex(k[1], k[2]);
+        } else {
+            const int lm = (size >> 2) - 1;
+            const bool lower = (lane & (size >> 3)) == 0;
+            const unsigned o0 = __shfl_xor_sync(kFull, k[3], lm);
+            const unsigned o1 = __shfl_xor_sync(kFull, k[2], lm);
+            const unsigned o2 = __shfl_xor_sync(kFull, k[1], lm);
+            const unsigned o3 = __shfl_xor_sync(kFull, k[0], lm);
+            k[0] = lower ? min(k[0], o0) : max(k[0], o0);
+            k[1] = lower ? min(k[1], o1) : max(k[1], o1);
+            k[2] = lower ? min(k[2], o2) : max(k[2], o2);
+            k[3] = lower ? min(k[3], o3) : max(k[3], o3);
+        }
 #pragma unroll
-        for (int j = size >> 1; j > 0; j >>= 1) {
+        for (int j = size >> 2; j > 0; j >>= 1) {
             if (j >= 4) {
                 const int lm = j >> 2;
-                const bool up = ((lane << 2) & size) == 0;
                 const bool lower = (lane & lm) == 0;
-                const bool keep_min = (lower == up);
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    unsigned o = __shfl_xor_sync(kFull, k[r], lm);
-                    k[r] = keep_min ? min(k[r], o) : max(k[r], o);
+                    const unsigned o = __shfl_xor_sync(kFull, k[r], lm);
+                    k[r] = lower ? min(k[r], o) : max(k[r], o);
                 }
+            } else if (j == 2) {
+                cex(k[0], k[2]);
+                cex(k[1], k[3]);
             } else {
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    if ((r & j) == 0) {
-                        const bool up = (((lane << 2) | r) & size) == 0;
-                        unsigned lo = min(k[r], k[r | j]), hi = max(k[r], k[r | j]);
-                        k[r] = up ? lo : hi;
-                        k[r | j] = up ? hi : lo;
-                    }
-                }
+                cex(k[0], k[1]);
+                cex(k[2], k[3]);
             }
         }
     }

@@ -135,6 +135,21 @@ struct Access {
     }
 };
 
+// Slot of the rising edge of the run that ends just below slot kf, walking the staged bitmap word by
+// word; -1 when the run is still high at slot 0 (its start lies outside the staged span).
+__device__ __forceinline__ int walk_back_smem(const unsigned *bits, int kf)
+{
+    const int top = kf - 1;
+    int w = top >> 5;
+    unsigned z = ~bits[w];
+    if ((top & 31) != 31) z &= (2u << (top & 31)) - 1u;
+    while (z == 0) {
+        if (--w < 0) return -1;
+        z = ~bits[w];
+    }
+    return w * 32 + (31 - __clz(z)) + 1;
+}
+
 // ---- long runs: warp-cooperative walk back to the rising edge ------------------------------------------
 // Fall at shared-memory slot kf (window index w0 + kf).  Returns false when the pulse has no rising edge
 // inside this window (framer.py:98-100).  All 32 lanes participate and get the same answer.
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
         unsigned F = ~W & (W << 1) & 0xffff0000u;
         unsigned R = W & ~(W << 1) & 0xffff0000u;
         const int k0 = kLeftHalo + c * 16;       // slot of chunk bit 0 (= W bit 16)
-        unsigned cm = 0, longf = 0;
+        unsigned cm = 0, longf = 0, lm = 0;
         if (fast) {
             if (R) tflags |= kFlagRise;
             if (F) tflags |= kFlagFall;
@@ -356,9 +371,27 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
                 C |= (acc & ~nxt) >> ((L + 1) >> 1);
                 acc &= nxt;
             }
-            longf = acc >> 16;                                  // runs longer than LMAX: deferred
+            // runs longer than LMAX: walk the staged bitmap in-thread; only runs that leave the staged
+            // span are deferred to the warp-cooperative path
+            unsigned lf = acc >> 16;
+            while (lf) {
+                const int b = __ffs(lf) - 1;
+                lf &= lf - 1;
+                const int kf = k0 + b;
+                const int r = walk_back_smem(sm.bits, kf);
+                if (r < 0) {
+                    longf |= 1u << b;
+                    continue;
+                }
+                const int kp = (r + kf) >> 1;                   // framer.py:113
+                tmax = kp > tmax ? kp : tmax;
+                if (preamble_match<G::H>(sm.mag + kp, h)) {
+                    cm |= 1u << b;
+                    if (kp < kNoise) lm |= 1u << b;             // noise window leaves the staged span
+                }
+            }
             if (C) {
-                tmax = k0 + (31 - __clz(C)) - 16;
+                tmax = max(tmax, k0 + (31 - __clz(C)) - 16);
                 // dense pre-filter: taps 3,4,5 must not exceed half the centre sample (framer.py:141,50)
                 float vals[G::NV * 4];
 #pragma unroll
@@ -429,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
             }
         }
         cmask[ci] = cm;
+        lmask[ci] = lm;
     }
 
     // ---- long runs (rare): one warp per deferred fall ----
@@ -496,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
             const int c = tid + ci * kThreads;
             if (c < T / 16) {
                 cmask[ci] |= sm.xmask[c];
-                lmask[ci] = sm.xlong[c];
+                lmask[ci] |= sm.xlong[c];
             }
         }
     } else if (tid == 0) {
@@ -514,7 +548,13 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
         while (cm) {
             const int b = __ffs(cm) - 1;
             cm &= cm - 1;
-            sm.list[off++] = (unsigned short)((k0 + b) | (((lmask[ci] >> b) & 1u) << 15));
+            const int kf = k0 + b;
+            unsigned short ent = (unsigned short)(kf | 0x8000);
+            if (!((lmask[ci] >> b) & 1u)) {
+                const int r = walk_back_smem(sm.bits, kf);       // >= 0: resolved in-thread above
+                ent = (unsigned short)((r + kf) >> 1);
+            }
+            sm.list[off++] = ent;
         }
         n_cand += total;
     }
@@ -573,11 +613,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
                 slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, P.sps, h, lane, crc_t, false, rec);
                 continue;
             }
-            // short run: recover the centre from the 32 bitmap bits below the fall
-            const int wq = kf >> 5, bq = kf & 31;
-            const unsigned Wv = __funnelshift_r(sm.bits[wq - 1], sm.bits[wq], bq);
-            const int run = __clz(~Wv);
-            const int kp = kf - ((run + 1) >> 1);
+            const int kp = kf;                                  // list holds the centre slot
             const float *mp = sm.mag + kp;
             slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kp, SPS ? SPS : P.sps, h, lane, crc_t, fast, rec);
         }
