@@ -10,7 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libadsb_b200.so")
+LIB_PATH = os.environ.get("ADSB_B200_LIB", os.path.join(CSRC, "libadsb_b200.so"))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "adsb_b200.h")
 
 ADSB_OK = 0

@@ -113,6 +113,9 @@ cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s
         cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, C64>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(scan_slice_kernel<SPS, C64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         configured = smem;
     }
     scan_slice_kernel<SPS, C64><<<n_blocks, kThreads, smem, s>>>(P);

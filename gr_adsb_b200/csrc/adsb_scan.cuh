@@ -35,6 +35,9 @@ __host__ __device__ inline int right_halo(int sps)
     return sps == 2 ? 384 : sps == 4 ? 640 : sps == 8 ? 1152 : ((120 * sps + 31) / 32) * 32;
 }
 
+#ifndef ADSB_MIN_CTAS
+#define ADSB_MIN_CTAS 6      // resident CTAs per SM the 4096-sample tile kernels are compiled for
+#endif
 constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
 
 // ---- shared-memory layout ------------------------------------------------------------------------
@@ -87,7 +90,7 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
 }
 
 // scratch slots
-enum { kScrTile = 12, kScrOff = 13, kScrSlowN = 14 };
+enum { kScrTile = 12, kScrOff = 13, kScrSlowN = 14, kScrNCand = 15 };
 
 // ---- preamble test -----------------------------------------------------------------------------------
 // framer.py:137-147 -- taps x[p + k*h], k = 0..15, against half the centre amplitude; template
@@ -262,7 +265,7 @@ __device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, lo
 
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int SPS, bool C64>
-__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_slice_kernel(const ScanParams P)
+__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : 2) scan_slice_kernel(const ScanParams P)
 {
     using G = Geo<SPS>;
     constexpr int T = G::T;
@@ -404,9 +407,9 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
                 for (int j = 0; j < 15 + G::DB; j++) {
                     const int i0 = 4 - G::DB + j;                 // index of position k0 - DB + j in vals
                     const float half = __fmul_rn(vals[i0], 0.5f);
-                    const bool ok = !(vals[i0 + 3 * G::H] > half) && !(vals[i0 + 4 * G::H] > half) &&
-                                    !(vals[i0 + 5 * G::H] > half);
-                    Q |= ok ? (1u << (16 - G::DB + j)) : 0u;
+                    // none of the three taps may exceed half (NaN taps count as low, like `tap > half`)
+                    const float m3 = fmaxf(fmaxf(vals[i0 + 3 * G::H], vals[i0 + 4 * G::H]), vals[i0 + 5 * G::H]);
+                    Q |= !(m3 > half) ? (1u << (16 - G::DB + j)) : 0u;
                 }
                 unsigned Tm = C & Q;
                 while (Tm) {
@@ -537,61 +540,95 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? 4 : 2) scan_
         s_max_long = -1;
     }
 
-    // ---- ordered compaction of this tile's candidates into sm.list ----
-    int n_cand = 0;
+    // ---- ordered compaction of this tile's candidates into sm.list; per-tile reductions ----
+    __shared__ int s_cnt[NCH][kWarps];
+    __shared__ int s_max[kWarps];
+    __shared__ unsigned s_flag[kWarps];
+    int wtot[NCH];
 #pragma unroll
-    for (int ci = 0; ci < NCH; ci++) {
-        int total;
-        int off = n_cand + block_excl_scan(__popc(cmask[ci]), sm.scratch, total);
-        unsigned cm = cmask[ci];
-        const int k0 = kLeftHalo + (tid + ci * kThreads) * 16;
-        while (cm) {
-            const int b = __ffs(cm) - 1;
-            cm &= cm - 1;
-            const int kf = k0 + b;
-            unsigned short ent = (unsigned short)(kf | 0x8000);
-            if (!((lmask[ci] >> b) & 1u)) {
-                const int r = walk_back_smem(sm.bits, kf);       // >= 0: resolved in-thread above
-                ent = (unsigned short)((r + kf) >> 1);
-            }
-            sm.list[off++] = ent;
-        }
-        n_cand += total;
-    }
-
-    // ---- per-tile reductions: edge flags, last pulse; candidate slot allocation ----
+    for (int ci = 0; ci < NCH; ci++) wtot[ci] = __reduce_add_sync(kFull, __popc(cmask[ci]));
     {
-        __shared__ int s_max[kWarps];
-        __shared__ unsigned s_flag[kWarps];
         const unsigned f = __reduce_or_sync(kFull, tflags);
         const int m = __reduce_max_sync(kFull, tmax);
         if (lane == 0) {
+#pragma unroll
+            for (int ci = 0; ci < NCH; ci++) s_cnt[ci][wid] = wtot[ci];
             s_flag[wid] = f;
             s_max[wid] = m;
         }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned ff = 0;
-            int mi = -1;
+    }
+    __syncthreads();
+    // candidates are rare: only warps that hold some compute their slots
+    bool any_here = false;
+#pragma unroll
+    for (int ci = 0; ci < NCH; ci++) any_here |= wtot[ci] != 0;
+    if (any_here) {
+        int base = 0;
+#pragma unroll
+        for (int ci = 0; ci < NCH; ci++) {
+            int before = 0, total = 0;
 #pragma unroll
             for (int q = 0; q < kWarps; q++) {
-                ff |= s_flag[q];
-                mi = s_max[q] > mi ? s_max[q] : mi;
+                const int v = s_cnt[ci][q];
+                before += (q < wid) ? v : 0;
+                total += v;
             }
-            long long mm = (mi >= 0) ? (w0 + mi) : -1;
-            mm = s_max_long > mm ? s_max_long : mm;
-            if (ff) atomicOr(&P.hdr->flags, ff);
-            if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
-            unsigned off = 0;
-            if (n_cand > 0) off = (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
-            P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
-            sm.scratch[kScrOff] = (int)off;
-            // x[n_out - 1] for the carried prev_in0 (framer.py:87)
-            const long long kl = (P.own_hi - 1) - w0;
-            if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
+            if (wtot[ci]) {
+                const int cnt = __popc(cmask[ci]);
+                int inc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(kFull, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                int off = base + before + inc - cnt;
+                unsigned cm = cmask[ci];
+                const int k0 = kLeftHalo + (tid + ci * kThreads) * 16;
+                while (cm) {
+                    const int b = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const int kf = k0 + b;
+                    unsigned short ent = (unsigned short)(kf | 0x8000);
+                    if (!((lmask[ci] >> b) & 1u)) {
+                        const int r = walk_back_smem(sm.bits, kf);       // >= 0: resolved in-thread above
+                        ent = (unsigned short)((r + kf) >> 1);
+                    }
+                    sm.list[off++] = ent;
+                }
+            }
+            base += total;
         }
-        __syncthreads();
     }
+    int n_cand = 0;
+    if (tid < 32) {
+        int v = 0;
+#pragma unroll
+        for (int ci = 0; ci < NCH; ci++) v += (lane < kWarps) ? s_cnt[ci][lane] : 0;
+        n_cand = __reduce_add_sync(kFull, v);
+    }
+    if (tid == 0) {
+        unsigned ff = 0;
+        int mi = -1;
+#pragma unroll
+        for (int q = 0; q < kWarps; q++) {
+            ff |= s_flag[q];
+            mi = s_max[q] > mi ? s_max[q] : mi;
+        }
+        long long mm = (mi >= 0) ? (w0 + mi) : -1;
+        mm = s_max_long > mm ? s_max_long : mm;
+        if (ff) atomicOr(&P.hdr->flags, ff);
+        if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
+        unsigned off = 0;
+        if (n_cand > 0) off = (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
+        P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
+        sm.scratch[kScrOff] = (int)off;
+        sm.scratch[kScrNCand] = n_cand;
+        // x[n_out - 1] for the carried prev_in0 (framer.py:87)
+        const long long kl = (P.own_hi - 1) - w0;
+        if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
+    }
+    __syncthreads();
+    n_cand = sm.scratch[kScrNCand];
     if (n_cand == 0) return;
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
 
