@@ -36,7 +36,7 @@ __host__ __device__ inline int right_halo(int sps)
 }
 
 #ifndef ADSB_MIN_CTAS
-#define ADSB_MIN_CTAS 6      // resident CTAs per SM the 4096-sample tile kernels are compiled for
+#define ADSB_MIN_CTAS 8      // resident CTAs per SM the 4096-sample tile kernels are compiled for
 #endif
 constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
 
