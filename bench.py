@@ -134,9 +134,9 @@ def run_reference_arm(args):
     cal = synth.synth_numpy(1 << 17, sps=SPS, n_bursts=int((1 << 17) * DENSITY), seed=SEED)["iq"]
     dt = _cpu_worker((cal, 65536))[0]
     rate = len(cal) / dt
-    per_worker = int(max(1 << 14, min(1 << 22, rate * 100.0 / (args.steps + args.warmup))))
-    shards = [synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1 + i)["iq"]
-              for i in range(cores)]
+    per_worker = int(max(1 << 14, min(1 << 21, rate * 100.0 / (args.steps + args.warmup))))
+    one = synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1)["iq"]
+    shards = [one] * cores          # every core chews an independent copy of the same bounded sample
     log("reference arm: %d cores, %d samples per core per step" % (cores, per_worker))
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
@@ -332,7 +332,7 @@ def main():
 
     # ---- bounded CPU baseline on the host cores (rank 0, N = 1)
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = 1 << 22
+        n_cpu = 1 << 25
         iq_cpu = shard[:n_cpu].cpu().numpy().view(np.complex64).reshape(-1)
         line["cpu_baseline"] = cpu_baseline_once(iq_cpu)
         line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
