@@ -176,6 +176,23 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     P.tile_tab = c->d_tile_tab;
     P.hdr = c->d_hdr;
     P.crc_tab = c->d_crc;
+    // tiles t with: t >= 1, (t+1)*T + rh <= n_arr, t*T + lead >= own_lo, (t+1)*T + lead <= own_hi
+    {
+        const long long T = c->T;
+        long long lo = 1;
+        const long long lo2 = (P.own_lo - P.lead + T - 1) / T;
+        if (lo2 > lo) lo = lo2;
+        long long hi = (P.n_arr - c->rh) / T - 1;
+        const long long hi2 = (P.own_hi - P.lead) / T - 1;
+        if (hi2 < hi) hi = hi2;
+        if (hi >= lo) {
+            P.fast_lo = (unsigned)lo;
+            P.fast_span = (unsigned)(hi - lo);
+        } else {
+            P.fast_lo = 0;
+            P.fast_span = 0xffffffffu;
+        }
+    }
     return P;
 }
 

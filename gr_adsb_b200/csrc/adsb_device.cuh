@@ -65,6 +65,8 @@ struct ScanParams {
     int rh;                // right halo, samples (multiple of 32, >= 120*sps)
     int left_is_start;     // window index 0 is where this work() call's window starts
     int prev_bit;          // bitmap value at window index -1 (framer.py:83-84)
+    unsigned fast_lo;      // tiles [fast_lo, fast_lo + fast_span] lie fully inside the array and the owned range
+    unsigned fast_span;    // (0xffffffff when there is none)
     int do_demod;
     int hist;              // 8*sps - 1
     Rec *cand;
@@ -86,6 +88,24 @@ __device__ __forceinline__ float ldg_stream_f1(const float *p)
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
+}
+
+__device__ __forceinline__ unsigned long long ldg_stream_b64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// |IQ|^2 of one complex64 held in a 64-bit register: one packed multiply (Blackwell mul.f32x2, both
+// lanes round-to-nearest like two FMULs) + one add -- same value as mag2() below
+__device__ __forceinline__ float mag2_packed(unsigned long long v)
+{
+    unsigned long long sq;
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(v));
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(sq));
+    return __fadd_rn(a, b);
 }
 
 // |IQ|^2 exactly as the oracle: fl32(fl32(re*re) + fl32(im*im)), no FMA contraction (adsb_rx.py:180)

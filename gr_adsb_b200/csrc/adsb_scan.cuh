@@ -116,6 +116,24 @@ __device__ __forceinline__ bool preamble_match(const float *m, int h_rt)
     return xp > half;
 }
 
+// same test for a centre that already passed the dense pre-filter (taps 3, 4, 5 known low)
+template <int HS>
+__device__ __forceinline__ bool preamble_match_rest(const float *m)
+{
+    const float xp = m[0];
+    const float half = __fmul_rn(xp, 0.5f);
+    if (!(m[2 * HS] > half)) return false;
+    if (!(m[7 * HS] > half)) return false;
+    if (!(m[9 * HS] > half)) return false;
+    if (m[1 * HS] > half) return false;
+    if (m[6 * HS] > half) return false;
+    if (m[8 * HS] > half) return false;
+#pragma unroll
+    for (int k = 10; k < 16; k++)
+        if (m[k * HS] > half) return false;
+    return xp > half;
+}
+
 __device__ __forceinline__ bool demod_in_range(const ScanParams &P, long long p)
 {
     // demod.py:67,82 in window coordinates: tag not late, last sample p + 119*sps + sps/2 inside in0
@@ -286,9 +304,8 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     const long long tile = sm.scratch[kScrTile];
     const long long a0 = tile * T;                 // array index of the tile's first owned sample
     const long long w0 = a0 + P.lead - kLeftHalo;  // window index of shared-memory slot 0
-    const bool interior = (a0 - kLeftHalo >= 0) && (a0 + T + rh <= P.n_arr) &&
-                          (w0 + kLeftHalo >= P.own_lo) && (w0 + kLeftHalo + T <= P.own_hi) && (w0 > 0);
-    const bool fast = SPS != 0 && interior;
+    // interior tile (host-computed range): staged span inside the array, chunk fully owned, w0 > 0
+    const bool fast = SPS != 0 && ((unsigned)tile - P.fast_lo) <= P.fast_span && P.fast_span != 0xffffffffu;
 
     // ---- phase 1: HBM -> |IQ|^2 tile + threshold bitmap ----
     if (fast) {
@@ -297,14 +314,14 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
             const float2 *src = reinterpret_cast<const float2 *>(P.in) + (a0 - kLeftHalo) + tid;
 #pragma unroll
             for (int u0 = 0; u0 < G::NPT; u0 += U) {
-                float2 v[U];
+                unsigned long long v[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    if (u0 + u < G::NPT) v[u] = ldg_stream_f2(src + (u0 + u) * kThreads);
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_b64(src + (u0 + u) * kThreads);
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (u0 + u < G::NPT) {
-                        const float x = mag2(v[u]);
+                        const float x = mag2_packed(v[u]);
                         sm.mag[(u0 + u) * kThreads + tid] = x;
                         const unsigned w = __ballot_sync(kFull, x >= thr);
                         if (lane == 0) sm.bits[(u0 + u) * kWarps + wid] = w;
@@ -381,10 +398,15 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
                 const int b = __ffs(lf) - 1;
                 lf &= lf - 1;
                 const int kf = k0 + b;
-                const int r = walk_back_smem(sm.bits, kf);
-                if (r < 0) {
-                    longf |= 1u << b;
-                    continue;
+                const int pos = 16 + b;
+                const int run = __clz(~(W << (32 - pos)));      // ones below the fall inside W
+                int r = kf - run;
+                if (run >= pos) {                               // run leaves W: walk the staged bitmap
+                    r = walk_back_smem(sm.bits, kf);
+                    if (r < 0) {
+                        longf |= 1u << b;
+                        continue;
+                    }
                 }
                 const int kp = (r + kf) >> 1;                   // framer.py:113
                 tmax = kp > tmax ? kp : tmax;
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
                 while (Tm) {
                     const int pc = 31 - __clz(Tm);
                     Tm &= ~(1u << pc);
-                    if (preamble_match<G::H>(sm.mag + k0 + pc - 16, h)) {
+                    if (preamble_match_rest<G::H>(sm.mag + k0 + pc - 16)) {
                         // key the candidate by its fall: first zero above the centre
                         const int fb = pc + __ffs(~(W >> (pc + 1)));
                         cm |= 1u << (fb - 16);
