@@ -281,6 +281,71 @@ __device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, lo
     if (lane < 4) rec.bits[lane] = pack_msb_first(lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]);
 }
 
+// Two candidates of an interior tile per warp (lanes 0-15 / 16-31): full 100-sample noise window, burst
+// fully staged, so no edge cases.  mp = shared-memory address of the candidate's centre sample.
+template <int SPS, bool C64>
+__device__ __forceinline__ void slice_pair(const ScanParams &P, const float *mp, long long p, int lane,
+                                           const unsigned (&crc16)[7], bool write, Rec &rec)
+{
+    constexpr int H = SPS / 2;
+    const int hl = lane & 15;
+    unsigned k[8];
+    bool nan = false;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int e = r * 16 + hl;
+        const float v = (e < kNoise) ? mp[e - kNoise] : 0.0f;
+        if (C64) {
+            // |IQ|^2 is never negative: the raw bits order like the values; NaN bits sort above +inf
+            k[r] = (e < kNoise) ? __float_as_uint(v) : 0x7f800000u;
+        } else {
+            nan |= (e < kNoise) && (v != v);
+            k[r] = (e < kNoise) ? f2key(v) : 0xffffffffu;
+        }
+    }
+    half_sort128(k, lane);
+    const int src = (lane & 16) | 6;                       // ranks 49, 50 -> position 8*6 + 1, 8*6 + 2
+    const unsigned ka = __shfl_sync(kFull, k[1], src), kb = __shfl_sync(kFull, k[2], src);
+    float med;
+    if (C64) {
+        const unsigned top = __shfl_sync(kFull, k[7], (lane & 16) | 15);
+        med = __fmul_rn(__fadd_rn(__uint_as_float(ka), __uint_as_float(kb)), 0.5f);   // fl32(fl32(a+b)/2)
+        if (top > 0x7f800000u) med = __int_as_float(0x7fc00000);
+    } else {
+        const unsigned anyn = __ballot_sync(kFull, nan);
+        med = __fmul_rn(__fadd_rn(key2f(ka), key2f(kb)), 0.5f);
+        if ((anyn >> (lane & 16)) & 0xffffu) med = __int_as_float(0x7fc00000);
+    }
+    const float xp = mp[0];
+    unsigned flags = 0;
+    unsigned w[4] = {0u, 0u, 0u, 0u};
+    if (P.do_demod) {
+        flags = kHitDemodValid;
+        const float *sob = mp + 8 * SPS;                       // demod.py:75
+        unsigned syn = 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const int bi = j * 16 + hl;
+            const bool bit = sob[bi * SPS] > sob[bi * SPS + H];   // demod.py:87-95
+            const unsigned bal = __ballot_sync(kFull, bit);
+            w[j >> 1] |= ((bal >> (lane & 16)) & 0xffffu) << (16 * (j & 1));
+            syn ^= bit ? crc16[j] : 0u;
+        }
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) syn ^= __shfl_xor_sync(kFull, syn, d);
+        const unsigned df = __brev(w[0]) >> 27;
+        if (syn == 0 && df >= 17 && df <= 19) flags |= kHitCrcOk;    // decoder.py:667-685
+    }
+    if (write) {
+        if (hl == 0) {
+            rec.idx = P.base + p;
+            rec.snr = __fdiv_rn(xp, med);
+            rec.flags = flags;
+        }
+        if (hl < 4) rec.bits[hl] = pack_msb_first(hl == 0 ? w[0] : hl == 1 ? w[1] : hl == 2 ? w[2] : w[3]);
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int SPS, bool C64>
 __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : 2) scan_slice_kernel(const ScanParams P)
@@ -654,27 +719,43 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     if (n_cand == 0) return;
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
 
-    // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC, one warp per candidate ----
-    unsigned crc_t[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
+    // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
+    // interior tiles: two candidates per warp (half-warp each); edges / long runs: one warp per candidate
     const Access<C64> X{P, sm.mag, w0, S};
-
+    const int sps_rt = SPS ? SPS : P.sps;
     for (int b0 = 0; b0 < n_cand; b0 += kStage) {
         const int nb = min(kStage, n_cand - b0);
-        for (int c = wid; c < nb; c += kWarps) {
-            const unsigned e = sm.list[b0 + c];
-            const int kf = e & 0x7fff;
-            Rec &rec = sm.stage[c];
-            if (e >> 15) {
-                long long p;
-                resolve_long<C64>(P, sm, w0, kf, lane, p);
-                slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, P.sps, h, lane, crc_t, false, rec);
-                continue;
+        if (2 * wid < nb) {
+            unsigned crc_t[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
+            unsigned crc16[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) crc16[j] = P.crc_tab[j * 16 + (lane & 15)];
+            for (int c = 2 * wid; c < nb; c += 2 * kWarps) {
+                const bool two = c + 1 < nb;
+                const unsigned e0 = sm.list[b0 + c];
+                const unsigned e1 = two ? sm.list[b0 + c + 1] : e0;
+                if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
+                    const int kp = (lane & 16) ? (int)e1 : (int)e0;
+                    const int cc = c + ((lane >> 4) & (two ? 1 : 0));
+                    slice_pair<SPS ? SPS : 2, C64>(P, sm.mag + kp, w0 + kp, lane, crc16, two || !(lane & 16), sm.stage[cc]);
+                    continue;
+                }
+                for (int q = 0; q < (two ? 2 : 1); q++) {
+                    const unsigned e = q ? e1 : e0;
+                    const int kf = e & 0x7fff;
+                    Rec &rec = sm.stage[c + q];
+                    if (e >> 15) {
+                        long long p;
+                        resolve_long<C64>(P, sm, w0, kf, lane, p);
+                        slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
+                    } else {
+                        const float *mp = sm.mag + kf;              // list holds the centre slot
+                        slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
+                    }
+                }
             }
-            const int kp = kf;                                  // list holds the centre slot
-            const float *mp = sm.mag + kp;
-            slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kp, SPS ? SPS : P.sps, h, lane, crc_t, fast, rec);
         }
         __syncthreads();
         // coalesced copy-out: 2 x 16 bytes per record
