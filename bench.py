@@ -215,7 +215,7 @@ def main():
     NONE = sharding.NONE
     rounds = [0, 0]          # carry rounds, re-resolves
     info_dev = torch.zeros(3, dtype=torch.int64, device=dev)
-    gathered = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
+    gathered = torch.zeros(3 * world, dtype=torch.int64, device=dev)
 
     def step():
         if world > 1:
@@ -224,16 +224,13 @@ def main():
                            base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=sptr)
         if world == 1:
             return
-        # blanking carry (framer.py:121-123,165): resolve speculatively, gather, fix up where it matters
+        # blanking carry (framer.py:121-123,165): resolve speculatively, all-gather (first candidate, last
+        # hit) straight from device memory, re-run the two resolve kernels where the true state reaches in
         used = NONE
         while True:
-            stream.synchronize()
-            c, _ = ctx.burst_finish(fetch_hits=False)
-            first_g = geo["base"] + c["first_candidate"] if c["first_candidate"] >= 0 else NONE
-            last_g = geo["base"] + c["last_accept"] if c["last_accept"] >= 0 else NONE
-            info_dev.copy_(torch.tensor([first_g, last_g, used], dtype=torch.int64), non_blocking=False)
-            dist.all_gather(gathered, info_dev)
-            infos = [tuple(int(v) for v in t.tolist()) for t in gathered]
+            ctx.burst_export_carry_dev(used, info_dev.data_ptr(), stream=sptr)
+            dist.all_gather_into_tensor(gathered, info_dev)
+            infos = [tuple(r) for r in gathered.view(world, 3).tolist()]          # the step's one host sync
             e_in, need = sharding.carry_plan(infos, blank)
             rounds[0] += 1
             if not any(need):

@@ -55,7 +55,8 @@ _lib = None
 EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_create", "adsb_destroy",
            "adsb_last_error", "adsb_reset_state", "adsb_get_state", "adsb_set_state", "adsb_get_counters",
            "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish",
-           "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev"]
+           "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
+           "adsb_burst_export_carry_dev"]
 
 
 def lib():
@@ -96,6 +97,8 @@ def lib():
     L.adsb_burst_finish.argtypes = [vp, C.POINTER(Counters), vp, sz, C.POINTER(sz)]
     L.adsb_burst_reresolve_dev.restype = i32
     L.adsb_burst_reresolve_dev.argtypes = [vp, i64, vp]
+    L.adsb_burst_export_carry_dev.restype = i32
+    L.adsb_burst_export_carry_dev.argtypes = [vp, i64, vp, vp]
     L.adsb_profile_enable.restype = i32
     L.adsb_profile_enable.argtypes = [vp, i32]
     L.adsb_profile_last.restype = i32
@@ -245,6 +248,10 @@ def _profile_methods():
     def burst_reresolve_dev(self, eob_in, stream=0):
         self._check(lib().adsb_burst_reresolve_dev(self._h, int(eob_in), C.c_void_p(stream)))
     Context.burst_reresolve_dev = burst_reresolve_dev
+
+    def burst_export_carry_dev(self, used_global, dev_ptr, stream=0):
+        self._check(lib().adsb_burst_export_carry_dev(self._h, int(used_global), C.c_void_p(dev_ptr), C.c_void_p(stream)))
+    Context.burst_export_carry_dev = burst_export_carry_dev
     Context.profile_enable = profile_enable
     Context.profile_last = profile_last
 

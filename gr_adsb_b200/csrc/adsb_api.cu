@@ -30,6 +30,16 @@ __global__ void init_header_kernel(Header *h)
     h->first_cand = -1;
 }
 
+// multi-GPU blanking carry: (first candidate, last hit, incoming state assumed) in GLOBAL window coordinates,
+// kNone where absent -- the triple gr_adsb_b200/sharding.py:carry_plan consumes
+__global__ void export_carry_kernel(const Header *h, long long base, long long used_global, long long *out)
+{
+    const long long kNone = -(1LL << 62);
+    out[0] = h->first_cand >= 0 ? base + h->first_cand : kNone;
+    out[1] = h->last_accept >= 0 ? base + h->last_accept : kNone;
+    out[2] = used_global;
+}
+
 struct HostStage {
     Header hdr;
     Rec first[kFirstHits];
@@ -122,9 +132,11 @@ cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P, bool c64, unsigned n_blocks, cudaStream_t s)
+cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P0, bool c64, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
 {
     if (n_blocks == 0) return cudaSuccess;
+    ScanParams P = P0;
+    P.tile_first = tile_first;
     switch (c->sps) {
     case 2: return c64 ? launch_scan_t<2, true>(P, n_blocks, s) : launch_scan_t<2, false>(P, n_blocks, s);
     case 4: return c64 ? launch_scan_t<4, true>(P, n_blocks, s) : launch_scan_t<4, false>(P, n_blocks, s);
@@ -176,6 +188,10 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     P.tile_tab = c->d_tile_tab;
     P.hdr = c->d_hdr;
     P.crc_tab = c->d_crc;
+    {
+        const char *e = getenv("ADSB_PREFETCH_TILES");
+        P.prefetch_tiles = e ? (unsigned)atoi(e) : (unsigned)(c->num_sms * 2);
+    }
     // tiles t with: t >= 1, (t+1)*T + rh <= n_arr, t*T + lead >= own_lo, (t+1)*T + lead <= own_hi
     {
         const long long T = c->T;
@@ -481,7 +497,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
     if ((rc = begin_call(ctx, s))) return rc;
     ScanParams P = make_params(ctx, d_in, n_in, lead, n_out, halo_left, threshold, base, prev_bit, 1);
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], s));
-    CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)n_tiles, s));
+    CK(launch_scan(ctx, P, is_c64 != 0, 0u, (unsigned)n_tiles, s));
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], s));
     if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], s));
@@ -509,6 +525,16 @@ int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream)
     if (rc) return rc;
     ctx->last.eob_in = eob_in;
     ctx->last.stream = s;
+    return ADSB_OK;
+}
+
+int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_out3, void *stream)
+{
+    if (!ctx || !ctx->last.pending || !d_out3) return ADSB_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
+    export_carry_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, ctx->last.base, used_global, reinterpret_cast<long long *>(d_out3));
+    CK(cudaGetLastError());
     return ADSB_OK;
 }
 
@@ -590,7 +616,7 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
             CK(cudaEventRecord(ctx->ev[ring], ctx->copy_stream));
             CK(cudaStreamWaitEvent(s, ctx->ev[ring], 0));
             ring = (ring + 1) % kEvRing;
-            if (ready > tiles_done) CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)(ready - tiles_done), s));
+            if (ready > tiles_done) CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)tiles_done, (unsigned)(ready - tiles_done), s));
             tiles_done = ready;
         }
     }
@@ -621,7 +647,7 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
     CK(cudaMemcpyAsync(ctx->d_in, in0, n_in * 4, cudaMemcpyHostToDevice, s));
     if ((rc = begin_call(ctx, s))) return rc;
     ScanParams P = make_params(ctx, ctx->d_in, n_in, 0, n_out, 0, threshold, 0, prev_bit, 0);
-    CK(launch_scan(ctx, P, false, (unsigned)n_tiles, s));
+    CK(launch_scan(ctx, P, false, 0u, (unsigned)n_tiles, s));
     if ((rc = launch_resolve(ctx, n_tiles, 0, eob_in, s))) return rc;
     ctx->last.pending = true;
     ctx->last.n_out = (long long)n_out;

@@ -360,19 +360,26 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     const int h = SPS ? G::H : (P.sps >> 1);
     const float thr = P.thr;
 
-    // ---- tile id (ticket: tiles start in index order whatever the CTA dispatch order) ----
-    if (tid == 0) {
-        sm.scratch[kScrTile] = (int)atomicAdd(&P.hdr->tile_ticket, 1u);
-        sm.scratch[kScrSlowN] = 0;
-    }
-    __syncthreads();
-    const long long tile = sm.scratch[kScrTile];
+    // ---- tile id: launches cover consecutive tile ranges, P.tile_first = first tile of this launch ----
+    if (tid == 0) sm.scratch[kScrSlowN] = 0;
+    const long long tile = (long long)P.tile_first + blockIdx.x;
     const long long a0 = tile * T;                 // array index of the tile's first owned sample
     const long long w0 = a0 + P.lead - kLeftHalo;  // window index of shared-memory slot 0
     // interior tile (host-computed range): staged span inside the array, chunk fully owned, w0 > 0
     const bool fast = SPS != 0 && ((unsigned)tile - P.fast_lo) <= P.fast_span && P.fast_span != 0xffffffffu;
 
     // ---- phase 1: HBM -> |IQ|^2 tile + threshold bitmap ----
+    if (fast && P.prefetch_tiles) {
+        // pull the tile one wave of CTAs ahead into L2 (one 128-byte line per thread): by the time a CTA
+        // gets to it, its loads are L2 hits instead of HBM round trips
+        const long long ta = tile + P.prefetch_tiles;
+        if (((unsigned)ta - P.fast_lo) <= P.fast_span) {
+            const char *base = reinterpret_cast<const char *>(P.in) + (ta * T - kLeftHalo) * (C64 ? 8 : 4);
+            constexpr int kLines = (kLeftHalo + T + G::RH) * (C64 ? 8 : 4) / 128;
+            for (int l = tid; l < kLines; l += kThreads)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
+        }
+    }
     if (fast) {
         constexpr int U = 6;
         if (C64) {

@@ -134,6 +134,11 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
  * each call re-reads the counters of the latest resolve). */
 int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream);
 
+/* Multi-GPU: after adsb_burst_work_dev / adsb_burst_reresolve_dev, write (first candidate, last hit,
+ * used_global) in GLOBAL window coordinates (-(2^62) where absent) to the device array d_out3[3] on the
+ * same stream, ready to be all-gathered without a host round trip (gr_adsb_b200/sharding.py). */
+int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_out3, void *stream);
+
 /* Measurement hook for bench.py: when enabled, adsb_burst_work_dev records CUDA events on its launch
  * stream before the scan kernel, after it and after the resolve kernels; adsb_profile_last waits for
  * the last one and returns the two durations in milliseconds. */
