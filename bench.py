@@ -181,16 +181,22 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sps", type=int, default=SPS, help="samples per symbol (secondary workloads; default 2)")
+    ap.add_argument("--density", type=float, default=DENSITY, help="bursts per sample (default 5e-3 = 10k/s at 2 Msps)")
+    ap.add_argument("--f32", action="store_true", help="feed float32 |IQ|^2 instead of complex64 (BASELINE configs[0] layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
+    globals()["SPS"] = args.sps
+    globals()["DENSITY"] = args.density
 
     import torch
     import torch.distributed as dist
     import gr_adsb_b200 as g
     from gr_adsb_b200 import sharding, synth
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,6 +212,12 @@ def main():
     buf = torch.zeros((geo["n_in"], 2), dtype=torch.float32, device=dev)
     shard = buf[geo["left"]: geo["left"] + L]
     _, truth = synth.synth_torch(L, SPS, int(L * DENSITY), SEED + rank, dev, out=shard, return_truth=False)
+    is_c64 = 0 if args.f32 else 1
+    if args.f32:
+        work_buf = (buf[:, 0] * buf[:, 0] + buf[:, 1] * buf[:, 1]).contiguous()
+        shard = None
+        del buf
+        buf = work_buf
     ctx = g.Context(SPS, geo["n_in"], device=local)
     stream = torch.cuda.Stream(device=dev)      # a real (non-NULL) stream: kernels and timing events share it
     torch.cuda.set_stream(stream)
@@ -220,7 +232,7 @@ def main():
     def step():
         if world > 1:
             sharding.exchange_halos(buf, geo, dist)
-        ctx.burst_work_dev(buf.data_ptr(), 1, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
+        ctx.burst_work_dev(buf.data_ptr(), is_c64, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
                            base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=sptr)
         if world == 1:
             return
@@ -277,7 +289,7 @@ def main():
     ctx.profile_enable(True)
     scan_ms, res_ms = [], []
     for _ in range(min(args.steps, 50)):
-        ctx.burst_work_dev(buf.data_ptr(), 1, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
+        ctx.burst_work_dev(buf.data_ptr(), is_c64, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
                            base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=sptr)
         a, b = ctx.profile_last()
         scan_ms.append(a)
@@ -285,10 +297,10 @@ def main():
     ctx.profile_enable(False)
     scan_avg = float(np.mean(scan_ms))
     peak, peak_src = measured_peak()
-    alg_bytes = 8.0 * geo["n_out"]          # 8 B per complex64 sample, read once
+    alg_bytes = (8.0 if is_c64 else 4.0) * geo["n_out"]   # 8 B per complex64 (4 B per float32) sample, read once
     achieved = alg_bytes / (scan_avg * 1e-3) / 1e9
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "scan_slice_kernel<4096,1,c64>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "scan_slice_kernel<sps=%d,%s>" % (SPS, "complex64" if is_c64 else "float32"), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_avg,
@@ -297,15 +309,18 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(L, world),
-            "clocks": clocks, "gpu_launches": 5 * args.steps + 3 * rounds[1],
+            "clocks": clocks, "gpu_launches": 5 * args.steps + 3 * rounds[1] + rounds[0],
             "hits_per_step": n_hits, "candidates_per_step": n_cand, "crc_pass_per_step": n_crc,
             "crc_pass_bursts_per_s": n_crc / (ms_per_step * 1e-3),
             "roofline": roofline}
+    if args.sps != 2 or args.density != 5e-3 or args.f32:
+        line["config"]["workload"] = ("secondary workload (not the headline): %d Msps %s, %.3g bursts/sample, threshold %.3g, "
+                                      "whole-buffer semantics" % (SPS, "float32 |IQ|^2" if args.f32 else "complex64 IQ", DENSITY, THRESHOLD))
     if world > 1:
         line["carry"] = {"allgather_rounds_per_step": rounds[0] / args.steps, "reresolves_per_step": rounds[1] / args.steps}
 
     # ---- end to end through the C ABI with HOST buffers (H2D of the samples + D2H of the hits timed)
-    if rank == 0 and not args.no_e2e:
+    if rank == 0 and not args.no_e2e and is_c64:
         try:
             host = torch.empty((L, 2), dtype=torch.float32, pin_memory=True)
             host.copy_(shard)
@@ -328,7 +343,7 @@ def main():
             line["e2e"] = {"error": repr(e)}
 
     # ---- bounded CPU baseline on the host cores (rank 0, N = 1)
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and is_c64:
         n_cpu = 1 << 25
         iq_cpu = shard[:n_cpu].cpu().numpy().view(np.complex64).reshape(-1)
         line["cpu_baseline"] = cpu_baseline_once(iq_cpu)
