@@ -282,12 +282,13 @@ __device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, lo
 }
 
 // Two candidates of an interior tile per warp (lanes 0-15 / 16-31): full 100-sample noise window, burst
-// fully staged, so no edge cases.  mp = shared-memory address of the candidate's centre sample.
+// fully staged, so no edge cases.  mp = shared-memory address of the candidate's centre sample.  The work
+// of a pair is split into two independent roles taken by different warps: the noise median / SNR ratio,
+// and the PPM slice + CRC; they fill disjoint fields of the staged record.
 template <int SPS, bool C64>
-__device__ __forceinline__ void slice_pair(const ScanParams &P, const float *mp, long long p, int lane,
-                                           const unsigned (&crc16)[7], bool write, Rec &rec)
+__device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float *mp, long long p, int lane,
+                                               bool write, Rec &rec)
 {
-    constexpr int H = SPS / 2;
     const int hl = lane & 15;
     unsigned k[8];
     bool nan = false;
@@ -316,7 +317,18 @@ __device__ __forceinline__ void slice_pair(const ScanParams &P, const float *mp,
         med = __fmul_rn(__fadd_rn(key2f(ka), key2f(kb)), 0.5f);
         if ((anyn >> (lane & 16)) & 0xffffu) med = __int_as_float(0x7fc00000);
     }
-    const float xp = mp[0];
+    if (write && hl == 0) {
+        rec.idx = P.base + p;
+        rec.snr = __fdiv_rn(mp[0], med);       // ratio; the compact kernel applies 10*log10(.)+1.6
+    }
+}
+
+template <int SPS>
+__device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float *mp, int lane,
+                                                bool write, Rec &rec)
+{
+    constexpr int H = SPS / 2;
+    const int hl = lane & 15;
     unsigned flags = 0;
     unsigned w[4] = {0u, 0u, 0u, 0u};
     if (P.do_demod) {
@@ -329,7 +341,7 @@ __device__ __forceinline__ void slice_pair(const ScanParams &P, const float *mp,
             const bool bit = sob[bi * SPS] > sob[bi * SPS + H];   // demod.py:87-95
             const unsigned bal = __ballot_sync(kFull, bit);
             w[j >> 1] |= ((bal >> (lane & 16)) & 0xffffu) << (16 * (j & 1));
-            syn ^= bit ? crc16[j] : 0u;
+            syn ^= bit ? P.crc_tab[bi] : 0u;
         }
 #pragma unroll
         for (int d = 8; d > 0; d >>= 1) syn ^= __shfl_xor_sync(kFull, syn, d);
@@ -337,11 +349,7 @@ __device__ __forceinline__ void slice_pair(const ScanParams &P, const float *mp,
         if (syn == 0 && df >= 17 && df <= 19) flags |= kHitCrcOk;    // decoder.py:667-685
     }
     if (write) {
-        if (hl == 0) {
-            rec.idx = P.base + p;
-            rec.snr = __fdiv_rn(xp, med);
-            rec.flags = flags;
-        }
+        if (hl == 0) rec.flags = flags;
         if (hl < 4) rec.bits[hl] = pack_msb_first(hl == 0 ? w[0] : hl == 1 ? w[1] : hl == 2 ? w[2] : w[3]);
     }
 }
@@ -727,40 +735,43 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
 
     // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
-    // interior tiles: two candidates per warp (half-warp each); edges / long runs: one warp per candidate
+    // interior tiles: candidates go in pairs (half-warp each) and every pair is two tasks -- median/SNR and
+    // PPM slice/CRC -- spread over the eight warps; edges / long runs: one warp per candidate, both roles
     const Access<C64> X{P, sm.mag, w0, S};
     const int sps_rt = SPS ? SPS : P.sps;
     for (int b0 = 0; b0 < n_cand; b0 += kStage) {
         const int nb = min(kStage, n_cand - b0);
-        if (2 * wid < nb) {
+        const int n_tasks = ((nb + 1) >> 1) * 2;
+        for (int t = wid; t < n_tasks; t += kWarps) {
+            const int c = (t >> 1) * 2;
+            const bool two = c + 1 < nb;
+            const unsigned e0 = sm.list[b0 + c];
+            const unsigned e1 = two ? sm.list[b0 + c + 1] : e0;
+            if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
+                const int kp = (lane & 16) ? (int)e1 : (int)e0;
+                const int cc = c + ((lane >> 4) & (two ? 1 : 0));
+                const bool wr = two || !(lane & 16);
+                if (t & 1)
+                    slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, sm.stage[cc]);
+                else
+                    slice_pair_snr<SPS ? SPS : 2, C64>(P, sm.mag + kp, w0 + kp, lane, wr, sm.stage[cc]);
+                continue;
+            }
+            if (t & 1) continue;                            // generic path: the even task does both roles
             unsigned crc_t[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
-            unsigned crc16[7];
-#pragma unroll
-            for (int j = 0; j < 7; j++) crc16[j] = P.crc_tab[j * 16 + (lane & 15)];
-            for (int c = 2 * wid; c < nb; c += 2 * kWarps) {
-                const bool two = c + 1 < nb;
-                const unsigned e0 = sm.list[b0 + c];
-                const unsigned e1 = two ? sm.list[b0 + c + 1] : e0;
-                if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
-                    const int kp = (lane & 16) ? (int)e1 : (int)e0;
-                    const int cc = c + ((lane >> 4) & (two ? 1 : 0));
-                    slice_pair<SPS ? SPS : 2, C64>(P, sm.mag + kp, w0 + kp, lane, crc16, two || !(lane & 16), sm.stage[cc]);
-                    continue;
-                }
-                for (int q = 0; q < (two ? 2 : 1); q++) {
-                    const unsigned e = q ? e1 : e0;
-                    const int kf = e & 0x7fff;
-                    Rec &rec = sm.stage[c + q];
-                    if (e >> 15) {
-                        long long p;
-                        resolve_long<C64>(P, sm, w0, kf, lane, p);
-                        slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
-                    } else {
-                        const float *mp = sm.mag + kf;              // list holds the centre slot
-                        slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
-                    }
+            for (int q = 0; q < (two ? 2 : 1); q++) {
+                const unsigned e = q ? e1 : e0;
+                const int kf = e & 0x7fff;
+                Rec &rec = sm.stage[c + q];
+                if (e >> 15) {
+                    long long p;
+                    resolve_long<C64>(P, sm, w0, kf, lane, p);
+                    slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
+                } else {
+                    const float *mp = sm.mag + kf;              // list holds the centre slot
+                    slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
                 }
             }
         }
