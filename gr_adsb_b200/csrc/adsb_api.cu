@@ -137,6 +137,7 @@ cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P0, bool c64, unsig
     if (n_blocks == 0) return cudaSuccess;
     ScanParams P = P0;
     P.tile_first = tile_first;
+    P.n_tiles_launch = n_blocks;
     switch (c->sps) {
     case 2: return c64 ? launch_scan_t<2, true>(P, n_blocks, s) : launch_scan_t<2, false>(P, n_blocks, s);
     case 4: return c64 ? launch_scan_t<4, true>(P, n_blocks, s) : launch_scan_t<4, false>(P, n_blocks, s);

@@ -66,6 +66,7 @@ struct ScanParams {
     int left_is_start;     // window index 0 is where this work() call's window starts
     int prev_bit;          // bitmap value at window index -1 (framer.py:83-84)
     unsigned tile_first;   // first tile of this launch (blockIdx.x is added)
+    unsigned n_tiles_launch;  // tiles covered by this launch
     unsigned prefetch_tiles;  // L2 prefetch distance in tiles (0 = off)
     unsigned fast_lo;      // tiles [fast_lo, fast_lo + fast_span] lie fully inside the array and the owned range
     unsigned fast_span;    // (0xffffffff when there is none)

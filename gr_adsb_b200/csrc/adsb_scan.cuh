@@ -49,7 +49,7 @@ struct TileSmem {
     unsigned short *xlong;  // T/16   which of them are long-run entries
     unsigned short *slow;   // kSlowCap fall slots
     Rec *stage;             // kStage
-    int *scratch;           // 16 ints
+    int *scratch;           // 64 ints: slots below + per-warp reduction cells
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -63,7 +63,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int T, int rh)
     b += align16((size_t)(T / 16) * 2) * 2;
     b += align16((size_t)kSlowCap * 2);
     b += (size_t)kStage * sizeof(Rec);
-    b += 16 * 4;
+    b += 64 * 4;
     return b;
 }
 
@@ -90,8 +90,16 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
 }
 
 // scratch slots
-enum { kScrTile = 12, kScrOff = 13, kScrSlowN = 14, kScrNCand = 15 };
+enum { kScrFast = 11, kScrTile = 12, kScrOff = 13, kScrSlowN = 14, kScrNCand = 15,
+       kScrCnt = 16 /* [2][8] */, kScrMax = 32 /* [8] */, kScrFlag = 40 /* [8] */, kScrMaxLong = 48 /* long long */ };
 
+// ---- thread-group barrier: scan_tile / slice_tile are written against this interface so that the phases can
+// be moved to warp groups with named barriers; a persistent 8+4-warp producer/consumer variant was measured in
+// round 1 and lost to the plain one-CTA-per-tile kernel (0.93 ms vs 0.61 ms: half the scanning warps per SM).
+struct CtaBar {
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ bool sync_or(bool p) const { return __syncthreads_or(p) != 0; }
+};
 // ---- preamble test -----------------------------------------------------------------------------------
 // framer.py:137-147 -- taps x[p + k*h], k = 0..15, against half the centre amplitude; template
 // [1,0,1,0,0,0,0,1,0,1,0,0,0,0,0,0] (framer.py:50).
@@ -354,23 +362,20 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
     }
 }
 
-// ---- the kernel ------------------------------------------------------------------------------------
-template <int SPS, bool C64>
-__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : 2) scan_slice_kernel(const ScanParams P)
+// ---- phases 1 + 2 of one tile, by the 256 scan threads (threads 0..255 of the CTA) --------------------------
+// On return (after the caller's next group barrier) sm.list, scratch[kScrNCand|kScrOff|kScrFast] are valid.
+template <int SPS, bool C64, class GB>
+__device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const GB gb)
 {
     using G = Geo<SPS>;
     constexpr int T = G::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int rh = SPS ? G::RH : P.rh;
-    const TileSmem sm = carve(smem_raw, T, rh);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;      // scan threads are threads 0..255
     const int S = kLeftHalo + T + rh;
     const int h = SPS ? G::H : (P.sps >> 1);
     const float thr = P.thr;
 
-    // ---- tile id: launches cover consecutive tile ranges, P.tile_first = first tile of this launch ----
     if (tid == 0) sm.scratch[kScrSlowN] = 0;
-    const long long tile = (long long)P.tile_first + blockIdx.x;
     const long long a0 = tile * T;                 // array index of the tile's first owned sample
     const long long w0 = a0 + P.lead - kLeftHalo;  // window index of shared-memory slot 0
     // interior tile (host-computed range): staged span inside the array, chunk fully owned, w0 > 0
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
             if (lane == 0) sm.bits[k >> 5] = w;
         }
     }
-    __syncthreads();
+    gb.sync();
 
     // ---- phase 2: falls -> pulse centres -> preamble match ----
     // Each thread owns the falls of 16-sample chunks; W holds the chunk in bits 16..31 and the 16 samples
@@ -571,14 +576,14 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     }
 
     // ---- long runs (rare): one warp per deferred fall ----
-    __shared__ long long s_max_long;
-    if (__syncthreads_or(have_long)) {
+    long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + kScrMaxLong);
+    if (gb.sync_or(have_long)) {
         for (int c = tid; c < T / 16; c += kThreads) {
             sm.xmask[c] = 0;
             sm.xlong[c] = 0;
         }
         if (tid == 0) s_max_long = -1;
-        __syncthreads();
+        gb.sync();
         const int n_slow = sm.scratch[kScrSlowN];
         const Access<C64> X{P, sm.mag, w0, S};
         if (n_slow <= kSlowCap) {
@@ -629,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
                 }
             }
         }
-        __syncthreads();
+        gb.sync();
 #pragma unroll
         for (int ci = 0; ci < NCH; ci++) {
             const int c = tid + ci * kThreads;
@@ -643,9 +648,9 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     }
 
     // ---- ordered compaction of this tile's candidates into sm.list; per-tile reductions ----
-    __shared__ int s_cnt[NCH][kWarps];
-    __shared__ int s_max[kWarps];
-    __shared__ unsigned s_flag[kWarps];
+    int (*s_cnt)[kWarps] = reinterpret_cast<int (*)[kWarps]>(sm.scratch + kScrCnt);
+    int *s_max = sm.scratch + kScrMax;
+    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + kScrFlag);
     int wtot[NCH];
 #pragma unroll
     for (int ci = 0; ci < NCH; ci++) wtot[ci] = __reduce_add_sync(kFull, __popc(cmask[ci]));
@@ -659,7 +664,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
             s_max[wid] = m;
         }
     }
-    __syncthreads();
+    gb.sync();
     // candidates are rare: only warps that hold some compute their slots
     bool any_here = false;
 #pragma unroll
@@ -725,13 +730,29 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
         P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
         sm.scratch[kScrOff] = (int)off;
         sm.scratch[kScrNCand] = n_cand;
+        sm.scratch[kScrFast] = fast ? 1 : 0;
         // x[n_out - 1] for the carried prev_in0 (framer.py:87)
         const long long kl = (P.own_hi - 1) - w0;
         if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
     }
-    __syncthreads();
-    n_cand = sm.scratch[kScrNCand];
+}
+
+// ---- phase 3 of one tile, by a group of n_warps warps (gtid = thread index inside the group; needs
+// n_warps * 32 >= 2 * kStage for the copy-out) ------------------------------------------------------------------
+template <int SPS, bool C64, class GB>
+__device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const int tid,
+                                           const int n_warps, const GB gb)
+{
+    using G = Geo<SPS>;
+    constexpr int T = G::T;
+    const int rh = SPS ? G::RH : P.rh;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int S = kLeftHalo + T + rh;
+    const int h = SPS ? G::H : (P.sps >> 1);
+    const long long w0 = tile * T + P.lead - kLeftHalo;
+    const int n_cand = sm.scratch[kScrNCand];
     if (n_cand == 0) return;
+    const bool fast = sm.scratch[kScrFast] != 0;
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
 
     // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
@@ -742,7 +763,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     for (int b0 = 0; b0 < n_cand; b0 += kStage) {
         const int nb = min(kStage, n_cand - b0);
         const int n_tasks = ((nb + 1) >> 1) * 2;
-        for (int t = wid; t < n_tasks; t += kWarps) {
+        for (int t = wid; t < n_tasks; t += n_warps) {
             const int c = (t >> 1) * 2;
             const bool two = c + 1 < nb;
             const unsigned e0 = sm.list[b0 + c];
@@ -775,7 +796,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
                 }
             }
         }
-        __syncthreads();
+        gb.sync();
         // coalesced copy-out: 2 x 16 bytes per record
         if (tid < nb * 2) {
             const unsigned slot = g_off + b0 + (tid >> 1);
@@ -784,8 +805,21 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
             else if ((tid & 1) == 0)
                 atomicOr(&P.hdr->flags, kFlagCandOverflow);
         }
-        __syncthreads();
+        if (b0 + kStage < n_cand) gb.sync();            // the staging area is reused by the next batch
     }
+}
+
+// ---- the kernel: one CTA (8 warps) per tile, phases in sequence ---------------------------------------------
+template <int SPS, bool C64>
+__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : 2) scan_slice_kernel(const ScanParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TileSmem sm = carve(smem_raw, Geo<SPS>::T, SPS ? Geo<SPS>::RH : P.rh);
+    const long long tile = (long long)P.tile_first + blockIdx.x;
+    const CtaBar gb;
+    scan_tile<SPS, C64>(P, sm, tile, gb);
+    gb.sync();
+    slice_tile<SPS, C64>(P, sm, tile, (int)threadIdx.x, kWarps, gb);
 }
 
 }  // namespace adsb
