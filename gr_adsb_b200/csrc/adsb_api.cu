@@ -402,6 +402,10 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
 
     // candidates: at most one per 2 samples in theory, ~1 per 600 on busy air; size for 1 per 16.
     size_t cap = max_items / 16 + 4096;
+    {
+        const size_t blocks = (max_items / (size_t)tile_items(sps) + 4) * (size_t)kTileSlots;   // fixed per-tile blocks
+        if (cap < 2 * blocks) cap = 2 * blocks;
+    }
     if (cap > 0x7fffff00u) cap = 0x7fffff00u;
     ctx->cand_cap = (unsigned)cap;
     ctx->hit_cap = (unsigned)cap;

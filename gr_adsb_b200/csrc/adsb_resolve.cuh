@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const ResolveParams P)
             if (lane == 0) s_excl = e;
         }
         __syncthreads();
+        // the last chunk knows the total: K1 only used hdr->n_cand as its overflow allocator
+        if (chunk == n_chunks - 1 && tid == 0) P.hdr->n_cand = (unsigned long long)s_excl + (unsigned long long)total;
         unsigned dst = s_excl + (unsigned)off;
 #pragma unroll
         for (int q = 0; q < 4; q++) {

@@ -14,6 +14,10 @@
 
 namespace adsb {
 
+#ifndef ADSB_LMAX2
+#define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
+#endif
+
 // ---- compile-time geometry per samples-per-symbol ------------------------------------------------------
 template <int SPS>
 struct Geo {
@@ -23,7 +27,7 @@ struct Geo {
     static constexpr int RH = SPS == 2 ? 384 : SPS == 4 ? 640 : SPS == 8 ? 1152 : 0;
     static constexpr int S = kLeftHalo + T + RH;
     static constexpr int NPT = S / kThreads;                           // slots per thread in phase 1
-    static constexpr int LMAX = SPS == 2 ? 4 : 8;                      // run lengths resolved bit-parallel
+    static constexpr int LMAX = ADSB_LMAX2 > 0 && SPS == 2 ? ADSB_LMAX2 : 8;   // run lengths resolved bit-parallel
     static constexpr int DB = LMAX / 2;                                // how far a centre lies before its chunk
     static constexpr int NV = (14 + 5 * H + 4 + 1 + 3) / 4;            // float4 loads of the dense pre-filter
     static_assert(SPS == 0 || (S % kThreads == 0 && RH >= 120 * SPS), "tile geometry");
@@ -38,6 +42,7 @@ __host__ __device__ inline int right_halo(int sps)
 #ifndef ADSB_MIN_CTAS
 #define ADSB_MIN_CTAS 8      // resident CTAs per SM the 4096-sample tile kernels are compiled for
 #endif
+constexpr int kTileSlots = 32;    // candidate records reserved per tile (typical busy tile: 5-10)
 constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
 
 // ---- shared-memory layout ------------------------------------------------------------------------
@@ -725,8 +730,11 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         mm = s_max_long > mm ? s_max_long : mm;
         if (ff) atomicOr(&P.hdr->flags, ff);
         if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
-        unsigned off = 0;
-        if (n_cand > 0) off = (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
+        // candidate records: a fixed block of kTileSlots per tile (no atomic round trip on the tile's critical
+        // path); the rare tile with more takes space from the overflow area behind the blocks
+        unsigned off = (unsigned)tile * kTileSlots;
+        if (n_cand > kTileSlots)
+            off = (unsigned)P.n_tiles_total * kTileSlots + (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
         P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
         sm.scratch[kScrOff] = (int)off;
         sm.scratch[kScrNCand] = n_cand;
