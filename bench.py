@@ -108,12 +108,12 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, len(r["tags"]), len(r["pdus"]), crc
 
 
-def cpu_baseline_once(iq, chunk=65536):
+def cpu_baseline_once(iq, chunk=None):
     """NumPy port of framer.py + demod.py (+ decoder.py's parity check) on one core."""
     dt, tags, pdus, crc = _cpu_worker((iq, chunk))
     return {"value": len(iq) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
-            "sample": "first %d samples of the rank-0 shard (complex64 -> |IQ|^2 -> framer+demod+CRC, work() chunks of %d), %.1f s"
-                      % (len(iq), chunk, dt),
+            "sample": "first %d samples of the rank-0 shard (complex64 -> |IQ|^2 -> framer+demod+CRC, %s), %.1f s"
+                      % (len(iq), "one work() call = whole-buffer semantics, as on the GPU" if chunk is None else "work() chunks of %d" % chunk, dt),
             "tags": tags, "pdus": pdus, "crc_pass": crc, "crc_pass_bursts_per_s": crc / dt}
 
 
@@ -132,7 +132,7 @@ def run_reference_arm(args):
         pass
     # calibrate on a small sample, then size the per-step sample so K+W steps take ~100 s
     cal = synth.synth_numpy(1 << 17, sps=SPS, n_bursts=int((1 << 17) * DENSITY), seed=SEED)["iq"]
-    dt = _cpu_worker((cal, 65536))[0]
+    dt = _cpu_worker((cal, None))[0]
     rate = len(cal) / dt
     per_worker = int(max(1 << 14, min(1 << 21, rate * 100.0 / (args.steps + args.warmup))))
     one = synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1)["iq"]
@@ -140,11 +140,11 @@ def run_reference_arm(args):
     log("reference arm: %d cores, %d samples per core per step" % (cores, per_worker))
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
-            pool.map(_cpu_worker, [(s, 65536) for s in shards])
+            pool.map(_cpu_worker, [(s, None) for s in shards])
         t0 = time.perf_counter()
         crc = 0
         for _ in range(args.steps):
-            out = pool.map(_cpu_worker, [(s, 65536) for s in shards])
+            out = pool.map(_cpu_worker, [(s, None) for s in shards])
             crc += sum(o[3] for o in out)
         dt = time.perf_counter() - t0
     total = per_worker * cores * args.steps
@@ -155,7 +155,7 @@ def run_reference_arm(args):
             "config": workload_config(per_worker * cores, 1),
             "crc_pass_bursts_per_s": crc / dt,
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                             "sample": "%d samples per core per step, %d cores, work() chunks of 65536 (oracle/adsb_oracle.py: "
+                             "sample": "%d samples per core per step, %d cores, one work() call per sample = whole-buffer semantics (oracle/adsb_oracle.py: "
                                        "NumPy restatement of framer.py+demod.py+CRC; the Python reference cannot travel to the GPU box)"
                                        % (per_worker, cores)},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
