@@ -235,12 +235,14 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     const long long gchunks = (n_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
     const unsigned cap_blocks = (unsigned)ctx->num_sms * 4u;
     unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
+    // compact: look-back depth grows with the number of concurrently running chunks -> one block per SM
+    const unsigned cblocks = (unsigned)ctx->num_sms;
     if (rerun)
         reset_resolve_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
     else
         gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
     chain_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
-    compact_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
+    compact_kernel<<<cblocks, kThreads, 0, s>>>(R);
     CK(cudaGetLastError());
     return ADSB_OK;
 }
@@ -411,7 +413,7 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->hit_cap = (unsigned)cap;
     ctx->tile_cap = max_items / ctx->T + 4;
     ctx->status_g_n = ctx->tile_cap / kTilesPerChunk + 4;
-    ctx->status_c_n = cap / kThreads + 4;
+    ctx->status_c_n = cap / kCandPerChunk + 4;
     ctx->tag_cap = 4096;
 #define ALLOC(ptr, bytes)                                                                       \
     if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return die(ADSB_E_NOMEM, #ptr, e)

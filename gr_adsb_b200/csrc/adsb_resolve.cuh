@@ -85,7 +85,7 @@ struct ResolveParams {
 };
 
 // ---- gather: order the tile blocks -------------------------------------------------------------------
-constexpr int kTilesPerChunk = kThreads * 4;
+constexpr int kTilesPerChunk = kThreads;      // one tile per thread: enough blocks to fill the GPU
 
 __global__ void __launch_bounds__(kThreads) gather_kernel(const ResolveParams P)
 {
@@ -98,16 +98,10 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const ResolveParams P)
         __syncthreads();
         const unsigned chunk = s_chunk;
         if (chunk >= n_chunks) break;
-        const long long t0 = (long long)chunk * kTilesPerChunk + tid * 4;
-        uint2 tt[4];
-        int cnt = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            tt[q] = (t0 + q < P.n_tiles) ? P.tile_tab[t0 + q] : make_uint2(0u, 0u);
-            cnt += (int)tt[q].y;
-        }
+        const long long t0 = (long long)chunk * kTilesPerChunk + tid;
+        const uint2 tt = (t0 < P.n_tiles) ? P.tile_tab[t0] : make_uint2(0u, 0u);
         int total;
-        int off = block_excl_scan(cnt, scratch, total);
+        const int off = block_excl_scan((int)tt.y, scratch, total);
         if (wid == 0) {
             unsigned e = lookback_exclusive(P.status_g, chunk, (unsigned)total, P.epoch, &P.hdr->flags);
             if (lane == 0) s_excl = e;
@@ -115,18 +109,18 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const ResolveParams P)
         __syncthreads();
         // the last chunk knows the total: K1 only used hdr->n_cand as its overflow allocator
         if (chunk == n_chunks - 1 && tid == 0) P.hdr->n_cand = (unsigned long long)s_excl + (unsigned long long)total;
-        unsigned dst = s_excl + (unsigned)off;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            for (unsigned s = 0; s < tt[q].y; s++) {
-                const unsigned src = tt[q].x + s;
-                if (src < P.cand_cap && dst < P.cand_cap) {
-                    const uint4 *a = reinterpret_cast<const uint4 *>(P.cand + src);
-                    uint4 *b = reinterpret_cast<uint4 *>(P.ord + dst);
-                    b[0] = a[0];
-                    b[1] = a[1];
-                }
-                dst++;
+        const unsigned dst = s_excl + (unsigned)off;
+        // warp-cooperative copy: the 32 tiles of a warp one after the other, 16 bytes per lane
+        const unsigned any = __ballot_sync(kFull, tt.y != 0);
+        for (unsigned m = any; m; m &= m - 1) {
+            const int t = __ffs(m) - 1;
+            const unsigned src_t = __shfl_sync(kFull, tt.x, t);
+            const unsigned cnt_t = __shfl_sync(kFull, tt.y, t);
+            const unsigned dst_t = __shfl_sync(kFull, dst, t);
+            for (unsigned i = lane; i < 2 * cnt_t; i += 32) {
+                const unsigned r = i >> 1;
+                if (src_t + r < P.cand_cap && dst_t + r < P.cand_cap)
+                    reinterpret_cast<uint4 *>(P.ord + dst_t + r)[i & 1] = reinterpret_cast<const uint4 *>(P.cand + src_t + r)[i & 1];
             }
         }
         __syncthreads();
@@ -189,6 +183,9 @@ __global__ void reset_resolve_kernel(Header *h)
 }
 
 // ---- compact: accepted candidates -> ordered hit list ------------------------------------------------
+constexpr int kCandPerThread = 4;
+constexpr int kCandPerChunk = kThreads * kCandPerThread;   // big chunks keep the look-back chain short
+
 __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P)
 {
     __shared__ int scratch[16];
@@ -196,53 +193,67 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned long long m64 = P.hdr->n_cand;
     const long long M = (long long)(m64 < P.cand_cap ? m64 : P.cand_cap);
-    const unsigned n_chunks = (unsigned)((M + kThreads - 1) / kThreads);
+    const unsigned n_chunks = (unsigned)((M + kCandPerChunk - 1) / kCandPerChunk);
     while (true) {
         if (tid == 0) s_chunk = atomicAdd(&P.hdr->chunk_ticket_c, 1u);
         __syncthreads();
         const unsigned chunk = s_chunk;
         if (chunk >= n_chunks) break;
-        const long long i = (long long)chunk * kThreads + tid;
-        Rec r;
-        r.flags = 0;
-        r.idx = -1;
-        if (i < M) {
-            const uint4 *a = reinterpret_cast<const uint4 *>(P.ord + i);
-            reinterpret_cast<uint4 *>(&r)[0] = a[0];
-            reinterpret_cast<uint4 *>(&r)[1] = a[1];
+        const long long i0 = (long long)chunk * kCandPerChunk + (long long)tid * kCandPerThread;
+        Rec r[kCandPerThread];
+        int acc = 0;
+        unsigned n_demod = 0, n_crc = 0;
+        long long mx = -1;
+#pragma unroll
+        for (int q = 0; q < kCandPerThread; q++) {
+            r[q].flags = 0;
+            r[q].idx = -1;
+            if (i0 + q < M) {
+                const uint4 *a = reinterpret_cast<const uint4 *>(P.ord + i0 + q);
+                reinterpret_cast<uint4 *>(&r[q])[0] = a[0];
+                reinterpret_cast<uint4 *>(&r[q])[1] = a[1];
+            }
+            if (r[q].flags & kAccepted) {
+                acc++;
+                n_demod += (r[q].flags & kHitDemodValid) ? 1u : 0u;
+                n_crc += (r[q].flags & kHitCrcOk) ? 1u : 0u;
+                mx = r[q].idx;                              // ascending: the last accepted one is the largest
+            }
         }
-        const int acc = (r.flags & kAccepted) ? 1 : 0;
         int total;
-        int off = block_excl_scan(acc, scratch, total);
+        const int off = block_excl_scan(acc, scratch, total);
         if (wid == 0) {
             unsigned e = lookback_exclusive(P.status_c, chunk, (unsigned)total, P.epoch, &P.hdr->flags);
             if (lane == 0) s_excl = e;
         }
         // block counters
-        const unsigned demod = __ballot_sync(kFull, acc && (r.flags & kHitDemodValid));
-        const unsigned crc = __ballot_sync(kFull, acc && (r.flags & kHitCrcOk));
-        long long mx = acc ? r.idx : -1;
+        n_demod = __reduce_add_sync(kFull, n_demod);
+        n_crc = __reduce_add_sync(kFull, n_crc);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             const long long o = __shfl_xor_sync(kFull, mx, d);
             mx = o > mx ? o : mx;
         }
         if (lane == 0) {
-            if (demod) atomicAdd(&P.hdr->n_demod, (unsigned long long)__popc(demod));
-            if (crc) atomicAdd(&P.hdr->n_crc, (unsigned long long)__popc(crc));
+            if (n_demod) atomicAdd(&P.hdr->n_demod, (unsigned long long)n_demod);
+            if (n_crc) atomicAdd(&P.hdr->n_crc, (unsigned long long)n_crc);
             if (mx >= 0) atomicMax(&P.hdr->last_accept, mx - P.base);
         }
         __syncthreads();
-        if (acc) {
-            const unsigned dst = s_excl + (unsigned)off;
-            if (dst < P.hit_cap) {
-                r.flags &= ~kAccepted;
-                r.snr = snr_db_from_ratio(r.snr);       // K1 left x[p]/median here
-                uint4 *b = reinterpret_cast<uint4 *>(P.hits + dst);
-                b[0] = reinterpret_cast<const uint4 *>(&r)[0];
-                b[1] = reinterpret_cast<const uint4 *>(&r)[1];
-            } else {
-                atomicOr(&P.hdr->flags, kFlagHitOverflow);
+        unsigned dst = s_excl + (unsigned)off;
+#pragma unroll
+        for (int q = 0; q < kCandPerThread; q++) {
+            if (r[q].flags & kAccepted) {
+                if (dst < P.hit_cap) {
+                    r[q].flags &= ~kAccepted;
+                    r[q].snr = snr_db_from_ratio(r[q].snr);       // K1 left x[p]/median here
+                    uint4 *b = reinterpret_cast<uint4 *>(P.hits + dst);
+                    b[0] = reinterpret_cast<const uint4 *>(&r[q])[0];
+                    b[1] = reinterpret_cast<const uint4 *>(&r[q])[1];
+                } else {
+                    atomicOr(&P.hdr->flags, kFlagHitOverflow);
+                }
+                dst++;
             }
         }
         if (tid == 0 && total) atomicAdd(&P.hdr->n_hits, (unsigned long long)total);
