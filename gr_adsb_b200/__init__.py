@@ -4,7 +4,7 @@
 (python/adsb/__init__.py:24-25); `Context` is the raw ctypes handle onto `include/adsb_b200.h`.
 """
 from ._native import Context, AdsbError, HIT_DTYPE, unpack_bits, build, lib  # noqa: F401
-from ._native import HIT_DEMOD_VALID, HIT_CRC_OK, HIT_LATE_TAG  # noqa: F401
+from ._native import HIT_DEMOD_VALID, HIT_CRC_OK, HIT_LATE_TAG, CARRY_USED_ON_DEVICE  # noqa: F401
 
 
 def __getattr__(name):

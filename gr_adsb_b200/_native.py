@@ -18,6 +18,7 @@ E_CAPACITY = -4
 HIT_DEMOD_VALID = 0x1
 HIT_CRC_OK = 0x2
 HIT_LATE_TAG = 0x4
+CARRY_USED_ON_DEVICE = -(1 << 63)
 
 HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
 assert HIT_DTYPE.itemsize == 32
@@ -27,6 +28,7 @@ class Counters(C.Structure):
     _fields_ = [("n_samples", C.c_uint64), ("n_candidates", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_demod", C.c_uint64), ("n_crc_ok", C.c_uint64), ("last_pulse", C.c_int64),
                 ("last_accept", C.c_int64), ("first_candidate", C.c_int64),
+                ("carry_unstable", C.c_uint32), ("reserved", C.c_uint32),
                 ("any_rise", C.c_uint32), ("any_fall", C.c_uint32)]
 
     def as_dict(self):
@@ -56,7 +58,7 @@ EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_creat
            "adsb_last_error", "adsb_reset_state", "adsb_get_state", "adsb_set_state", "adsb_get_counters",
            "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish",
            "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
-           "adsb_burst_export_carry_dev"]
+           "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev"]
 
 
 def lib():
@@ -99,6 +101,8 @@ def lib():
     L.adsb_burst_reresolve_dev.argtypes = [vp, i64, vp]
     L.adsb_burst_export_carry_dev.restype = i32
     L.adsb_burst_export_carry_dev.argtypes = [vp, i64, vp, vp]
+    L.adsb_burst_carry_round_dev.restype = i32
+    L.adsb_burst_carry_round_dev.argtypes = [vp, vp, i32, i32, i32, vp]
     L.adsb_profile_enable.restype = i32
     L.adsb_profile_enable.argtypes = [vp, i32]
     L.adsb_profile_last.restype = i32
@@ -252,6 +256,11 @@ def _profile_methods():
     def burst_export_carry_dev(self, used_global, dev_ptr, stream=0):
         self._check(lib().adsb_burst_export_carry_dev(self._h, int(used_global), C.c_void_p(dev_ptr), C.c_void_p(stream)))
     Context.burst_export_carry_dev = burst_export_carry_dev
+
+    def burst_carry_round_dev(self, gathered_ptr, world, rank, final_check=False, stream=0):
+        self._check(lib().adsb_burst_carry_round_dev(self._h, C.c_void_p(gathered_ptr), int(world), int(rank),
+                                                      1 if final_check else 0, C.c_void_p(stream)))
+    Context.burst_carry_round_dev = burst_carry_round_dev
     Context.profile_enable = profile_enable
     Context.profile_last = profile_last
 

@@ -24,20 +24,24 @@ constexpr int kEvRing = 4;
 
 __global__ void init_header_kernel(Header *h)
 {
+    const unsigned unstable = h->carry_unstable;       // sticky across calls until read by adsb_burst_finish
     memset(h, 0, sizeof(Header));
     h->last_pulse = -1;
     h->last_accept = -1;
     h->first_cand = -1;
+    h->carry_used = kCarryNone;
+    h->carry_ein = kCarryNone;
+    h->carry_unstable = unstable;
 }
 
 // multi-GPU blanking carry: (first candidate, last hit, incoming state assumed) in GLOBAL window coordinates,
 // kNone where absent -- the triple gr_adsb_b200/sharding.py:carry_plan consumes
-__global__ void export_carry_kernel(const Header *h, long long base, long long used_global, long long *out)
+__global__ void export_carry_kernel(const Header *h, long long base, long long used_global, int used_from_dev,
+                                    long long *out)
 {
-    const long long kNone = -(1LL << 62);
-    out[0] = h->first_cand >= 0 ? base + h->first_cand : kNone;
-    out[1] = h->last_accept >= 0 ? base + h->last_accept : kNone;
-    out[2] = used_global;
+    out[0] = h->first_cand >= 0 ? base + h->first_cand : kCarryNone;
+    out[1] = h->last_accept >= 0 ? base + h->last_accept : kCarryNone;
+    out[2] = used_from_dev ? h->carry_used : used_global;
 }
 
 struct HostStage {
@@ -213,7 +217,8 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     return P;
 }
 
-int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long eob_in, cudaStream_t s, bool rerun = false)
+int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long eob_in, cudaStream_t s, bool rerun = false,
+                   bool dev_carry = false)
 {
     ResolveParams R;
     memset(&R, 0, sizeof(R));
@@ -231,6 +236,7 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     R.base = base;
     R.eob_in = eob_in;
     R.blank = 63 * ctx->sps;
+    R.dev_carry = dev_carry ? 1 : 0;
     if (n_tiles <= 0) return ADSB_OK;
     const long long gchunks = (n_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
     const unsigned cap_blocks = (unsigned)ctx->num_sms * 4u;
@@ -238,7 +244,7 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     // compact: look-back depth grows with the number of concurrently running chunks -> one block per SM
     const unsigned cblocks = (unsigned)ctx->num_sms;
     if (rerun)
-        reset_resolve_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
+        reset_resolve_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, R.dev_carry);
     else
         gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
     chain_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
@@ -535,12 +541,29 @@ int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream)
     return ADSB_OK;
 }
 
+int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int world, int rank, int final_check,
+                               void *stream)
+{
+    if (!ctx || !ctx->last.pending || !d_gathered || world < 1 || rank < 0 || rank >= world) return ADSB_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
+    carry_plan_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, reinterpret_cast<const long long *>(d_gathered), world, rank,
+                                      63LL * ctx->sps, final_check);
+    CK(cudaGetLastError());
+    if (final_check) return ADSB_OK;
+    const long long n_tiles = tiles_for(ctx, ctx->last.n_out, ctx->last.lead);
+    int rc = bump_epoch(ctx, s);
+    if (rc) return rc;
+    return launch_resolve(ctx, n_tiles, ctx->last.base, 0, s, true, true);   // no-ops unless hdr->carry_need
+}
+
 int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_out3, void *stream)
 {
     if (!ctx || !ctx->last.pending || !d_out3) return ADSB_E_INVAL;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
-    export_carry_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, ctx->last.base, used_global, reinterpret_cast<long long *>(d_out3));
+    export_carry_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, ctx->last.base, used_global, used_global == ADSB_CARRY_USED_ON_DEVICE,
+                                        reinterpret_cast<long long *>(d_out3));
     CK(cudaGetLastError());
     return ADSB_OK;
 }
@@ -569,6 +592,7 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
     c.last_pulse = h.last_pulse;
     c.last_accept = h.last_accept;
     c.first_candidate = h.first_cand;
+    c.carry_unstable = h.carry_unstable;
     c.any_rise = (h.flags & kFlagRise) ? 1u : 0u;
     c.any_fall = (h.flags & kFlagFall) ? 1u : 0u;
     if (counters) *counters = c;

@@ -34,6 +34,7 @@ struct __align__(16) Rec {
 static_assert(sizeof(Rec) == 32, "record must stay 32 bytes");
 
 constexpr unsigned kHitDemodValid = 1u, kHitCrcOk = 2u, kHitLate = 4u;
+constexpr long long kCarryNone = -(1LL << 62);   // "no blanking state" / "no candidate" in the carry exchange
 
 struct Header {
     unsigned long long n_cand;       // candidates allocated by K1 (atomic)
@@ -49,6 +50,11 @@ struct Header {
     float x_last;                    // x[n_out-1]  -> framer.py:87 prev_in0
     unsigned pad;
     long long first_cand;            // first candidate centre, window coordinates (-1: none)
+    // multi-GPU blanking carry resolved on the device (global window coordinates)
+    long long carry_ein;             // incoming state the next conditional re-resolve must use
+    long long carry_used;            // incoming state the latest resolve assumed
+    int carry_need;                  // 1: the conditional re-resolve kernels must run
+    unsigned carry_unstable;         // rounds whose final check still found a rank needing a fix-up (sticky)
 };
 
 struct ScanParams {

@@ -82,6 +82,7 @@ struct ResolveParams {
     long long base;             // records carry base + window index
     long long eob_in;           // incoming prev_eob_idx, window coordinates (framer.py:57,121)
     int blank;                  // 63 * sps (framer.py:165)
+    int dev_carry;              // 1: conditional re-run -- take eob from hdr->carry_ein, do nothing unless hdr->carry_need
 };
 
 // ---- gather: order the tile blocks -------------------------------------------------------------------
@@ -135,9 +136,10 @@ constexpr unsigned kAccepted = 0x80000000u;
 
 __global__ void __launch_bounds__(kThreads) chain_kernel(const ResolveParams P)
 {
+    if (P.dev_carry && !P.hdr->carry_need) return;
     const unsigned long long m64 = P.hdr->n_cand;
     const long long M = (long long)(m64 < P.cand_cap ? m64 : P.cand_cap);
-    const long long e_in = P.base + P.eob_in;
+    const long long e_in = P.dev_carry ? P.hdr->carry_ein : P.base + P.eob_in;
     const long long D = P.blank;
     // every record's accepted bit is assigned exactly once per launch (by the record's own thread when
     // it is ineligible, otherwise by the head of its segment), so the kernel can be re-run with
@@ -173,8 +175,9 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const ResolveParams P)
 }
 
 // reset what compact_kernel accumulates, before a re-run of chain + compact
-__global__ void reset_resolve_kernel(Header *h)
+__global__ void reset_resolve_kernel(Header *h, int dev_carry)
 {
+    if (dev_carry && !h->carry_need) return;
     h->n_hits = 0;
     h->n_demod = 0;
     h->n_crc = 0;
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
     __shared__ int scratch[16];
     __shared__ unsigned s_chunk, s_excl;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (P.dev_carry && !P.hdr->carry_need) return;
     const unsigned long long m64 = P.hdr->n_cand;
     const long long M = (long long)(m64 < P.cand_cap ? m64 : P.cand_cap);
     const unsigned n_chunks = (unsigned)((M + kCandPerChunk - 1) / kCandPerChunk);
@@ -258,6 +262,36 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
         }
         if (tid == 0 && total) atomicAdd(&P.hdr->n_hits, (unsigned long long)total);
         __syncthreads();
+    }
+}
+
+// ---- multi-GPU blanking carry, resolved without a host round trip -----------------------------------------
+// gathered[r] = (first candidate, last hit, incoming state assumed) of shard r, global window coordinates,
+// kCarryNone where absent.  Same plan as gr_adsb_b200/sharding.py:carry_plan, evaluated by every rank.
+__global__ void carry_plan_kernel(Header *h, const long long *gathered, int world, int rank, long long blank,
+                                  int final_check)
+{
+    long long e = kCarryNone, my_e = kCarryNone;
+    int my_need = 0, any = 0;
+    for (int r = 0; r < world; r++) {
+        const long long first = gathered[3 * r], last = gathered[3 * r + 1], used = gathered[3 * r + 2];
+        const bool changed = e != used;
+        const long long mx = e > used ? e : used;
+        const bool need = changed && first != kCarryNone && first <= mx;
+        if (r == rank) {
+            my_e = e;
+            my_need = need;
+        }
+        any |= need;
+        if (last != kCarryNone) e = last + blank;
+    }
+    if (final_check) {
+        if (any) h->carry_unstable += 1;
+        h->carry_need = 0;
+    } else {
+        h->carry_need = my_need;
+        h->carry_ein = my_e;
+        h->carry_used = my_e;       // where no re-run is needed the result is the same under either value
     }
 }
 

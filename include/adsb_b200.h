@@ -67,6 +67,8 @@ typedef struct adsb_counters {
     int64_t last_pulse;     /* centre of the last complete pulse, -1 if none               */
     int64_t last_accept;    /* centre of the last hit, window coordinates, -1 if none       */
     int64_t first_candidate;/* centre of the first candidate, window coordinates, -1 if none */
+    uint32_t carry_unstable; /* device-side carry rounds whose final check still wanted a fix-up  */
+    uint32_t reserved;
     uint32_t any_rise;      /* framer.py:95 guard inputs                                   */
     uint32_t any_fall;
 } adsb_counters;
@@ -137,7 +139,16 @@ int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream);
 /* Multi-GPU: after adsb_burst_work_dev / adsb_burst_reresolve_dev, write (first candidate, last hit,
  * used_global) in GLOBAL window coordinates (-(2^62) where absent) to the device array d_out3[3] on the
  * same stream, ready to be all-gathered without a host round trip (gr_adsb_b200/sharding.py). */
+#define ADSB_CARRY_USED_ON_DEVICE INT64_MIN   /* used_global: take the value the device-side plan recorded */
 int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_out3, void *stream);
+
+/* Multi-GPU, no host round trip: d_gathered[world][3] is the all-gathered export of every shard.  Evaluates
+ * the carry plan on the device for shard `rank`; unless `final_check`, follows with the resolve kernels in
+ * conditional mode (they exit at once when this shard needs no fix-up).  With `final_check` nothing is
+ * re-run; if any shard would still need one, adsb_counters.carry_unstable is bumped (read it after the
+ * stream is idle: non-zero means more rounds were needed than were issued). */
+int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int world, int rank, int final_check,
+                               void *stream);
 
 /* Measurement hook for bench.py: when enabled, adsb_burst_work_dev records CUDA events on its launch
  * stream before the scan kernel, after it and after the resolve kernels; adsb_profile_last waits for

@@ -34,7 +34,7 @@ def test_hit_record_layout():
     assert g.HIT_DTYPE.itemsize == 32
     assert g.HIT_DTYPE.fields["idx"][1] == 0 and g.HIT_DTYPE.fields["snr"][1] == 8
     assert g.HIT_DTYPE.fields["flags"][1] == 12 and g.HIT_DTYPE.fields["bits"][1] == 16
-    assert ctypes.sizeof(_native.Counters) == 72
+    assert ctypes.sizeof(_native.Counters) == 80
 
 
 def test_strerror_and_bad_args():
