@@ -15,6 +15,7 @@
 using namespace adsb;
 
 static_assert(sizeof(adsb_hit) == sizeof(Rec), "adsb_hit layout");
+static_assert(kTilesPerChunk == kThreads, "K1 accumulates tile_chunk_tot[tile / kThreads]");
 
 namespace {
 
@@ -64,15 +65,14 @@ struct adsb_ctx {
     unsigned cand_cap, hit_cap;
     uint2 *d_tile_tab;
     size_t tile_cap;
-    unsigned long long *d_status_g, *d_status_c;
-    size_t status_g_n, status_c_n;
+    unsigned *d_tile_chunk_tot, *d_cand_chunk_tot;   // per-chunk totals (ordered offsets without look-back)
+    size_t tile_chunk_n, cand_chunk_n;
     Header *d_hdr;
     unsigned *d_crc;
     long long *d_sob;
     unsigned char *d_bits, *d_valid;
     size_t tag_cap;
     HostStage *h_stage;
-    unsigned epoch;
     int num_sms;
     // bookkeeping of the call in flight (adsb_burst_work_dev -> adsb_burst_finish)
     struct {
@@ -191,6 +191,7 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     P.cand = c->d_cand;
     P.cand_cap = c->cand_cap;
     P.tile_tab = c->d_tile_tab;
+    P.tile_chunk_tot = c->d_tile_chunk_tot;
     P.hdr = c->d_hdr;
     P.crc_tab = c->d_crc;
     {
@@ -229,10 +230,9 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     R.hits = ctx->d_hits;
     R.hit_cap = ctx->hit_cap;
     R.cand_cap = ctx->cand_cap;
-    R.status_g = ctx->d_status_g;
-    R.status_c = ctx->d_status_c;
+    R.tile_chunk_tot = ctx->d_tile_chunk_tot;
+    R.cand_chunk_tot = ctx->d_cand_chunk_tot;
     R.hdr = ctx->d_hdr;
-    R.epoch = ctx->epoch;
     R.base = base;
     R.eob_in = eob_in;
     R.blank = 63 * ctx->sps;
@@ -240,9 +240,8 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     if (n_tiles <= 0) return ADSB_OK;
     const long long gchunks = (n_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
     const unsigned cap_blocks = (unsigned)ctx->num_sms * 4u;
-    unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
-    // compact: look-back depth grows with the number of concurrently running chunks -> one block per SM
-    const unsigned cblocks = (unsigned)ctx->num_sms;
+    const unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
+    const unsigned cblocks = cap_blocks;
     if (rerun)
         reset_resolve_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, R.dev_carry);
     else
@@ -253,25 +252,23 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     return ADSB_OK;
 }
 
-int bump_epoch(adsb_ctx *ctx, cudaStream_t s)
+// zero the accepted-per-chunk totals chain_kernel accumulates (bounded by the candidates n_out items can hold)
+int zero_cand_totals(adsb_ctx *ctx, long long n_out, cudaStream_t s)
 {
-    // look-back status words carry the epoch, so nothing has to be cleared between calls
-    ctx->epoch = (ctx->epoch + 1) & 0x3fffffffu;
-    if (ctx->epoch == 0) {   // wrapped: stale status words could alias, clear them
-        CK(cudaMemsetAsync(ctx->d_status_g, 0, ctx->status_g_n * 8, s));
-        CK(cudaMemsetAsync(ctx->d_status_c, 0, ctx->status_c_n * 8, s));
-        ctx->epoch = 1;
-    }
+    size_t n = (size_t)(n_out / 2 / kCandPerChunk) + 2;
+    if (n > ctx->cand_chunk_n) n = ctx->cand_chunk_n;
+    CK(cudaMemsetAsync(ctx->d_cand_chunk_tot, 0, n * sizeof(unsigned), s));
     return ADSB_OK;
 }
 
-int begin_call(adsb_ctx *ctx, cudaStream_t s)
+int begin_call(adsb_ctx *ctx, long long n_tiles, long long n_out, cudaStream_t s)
 {
-    int rc = bump_epoch(ctx, s);
-    if (rc) return rc;
     init_header_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
     CK(cudaGetLastError());
-    return ADSB_OK;
+    size_t n = (size_t)(n_tiles / kTilesPerChunk) + 2;
+    if (n > ctx->tile_chunk_n) n = ctx->tile_chunk_n;
+    CK(cudaMemsetAsync(ctx->d_tile_chunk_tot, 0, n * sizeof(unsigned), s));
+    return zero_cand_totals(ctx, n_out, s);
 }
 
 int ensure_input(adsb_ctx *ctx, size_t bytes)
@@ -304,7 +301,6 @@ long long next_eob(const Header &h, long long eob_in, long long n_out, int sps)
 
 int status_of(adsb_ctx *ctx, const Header &h)
 {
-    if (h.flags & kFlagSpin) return fail(ctx, ADSB_E_INTERNAL, "look-back spin limit hit");
     if (h.flags & kFlagHalo) return fail(ctx, ADSB_E_HALO, "pulse run crosses the left halo edge");
     if (h.flags & (kFlagCandOverflow | kFlagHitOverflow)) return fail(ctx, ADSB_E_NOMEM, "candidate capacity exceeded (raise max_items)");
     return ADSB_OK;
@@ -351,8 +347,8 @@ void adsb_destroy(adsb_ctx *ctx)
     cudaFree(ctx->d_ord);
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_tile_tab);
-    cudaFree(ctx->d_status_g);
-    cudaFree(ctx->d_status_c);
+    cudaFree(ctx->d_tile_chunk_tot);
+    cudaFree(ctx->d_cand_chunk_tot);
     cudaFree(ctx->d_hdr);
     cudaFree(ctx->d_crc);
     cudaFree(ctx->d_sob);
@@ -418,8 +414,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->cand_cap = (unsigned)cap;
     ctx->hit_cap = (unsigned)cap;
     ctx->tile_cap = max_items / ctx->T + 4;
-    ctx->status_g_n = ctx->tile_cap / kTilesPerChunk + 4;
-    ctx->status_c_n = cap / kCandPerChunk + 4;
+    ctx->tile_chunk_n = ctx->tile_cap / kTilesPerChunk + 4;
+    ctx->cand_chunk_n = cap / kCandPerChunk + 4;
     ctx->tag_cap = 4096;
 #define ALLOC(ptr, bytes)                                                                       \
     if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return die(ADSB_E_NOMEM, #ptr, e)
@@ -427,8 +423,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ALLOC(ctx->d_ord, cap * sizeof(Rec));
     ALLOC(ctx->d_hits, cap * sizeof(Rec));
     ALLOC(ctx->d_tile_tab, ctx->tile_cap * sizeof(uint2));
-    ALLOC(ctx->d_status_g, ctx->status_g_n * 8);
-    ALLOC(ctx->d_status_c, ctx->status_c_n * 8);
+    ALLOC(ctx->d_tile_chunk_tot, ctx->tile_chunk_n * sizeof(unsigned));
+    ALLOC(ctx->d_cand_chunk_tot, ctx->cand_chunk_n * sizeof(unsigned));
     ALLOC(ctx->d_hdr, sizeof(Header));
     ALLOC(ctx->d_crc, kMsgBits * sizeof(unsigned));
     ALLOC(ctx->d_sob, ctx->tag_cap * sizeof(long long));
@@ -439,8 +435,6 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     unsigned tab[kMsgBits];
     crc_table(tab);
     if ((e = cudaMemcpy(ctx->d_crc, tab, sizeof(tab), cudaMemcpyHostToDevice)) != cudaSuccess) return die(ADSB_E_CUDA, "crc table", e);
-    if ((e = cudaMemset(ctx->d_status_g, 0, ctx->status_g_n * 8)) != cudaSuccess) return die(ADSB_E_CUDA, "memset", e);
-    if ((e = cudaMemset(ctx->d_status_c, 0, ctx->status_c_n * 8)) != cudaSuccess) return die(ADSB_E_CUDA, "memset", e);
     *out = ctx;
     return ADSB_OK;
 }
@@ -507,7 +501,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
     const int prev_bit = (lead != 0) ? (0.0f >= threshold) : (ctx->prev_in0 >= threshold);
     const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
     if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
-    if ((rc = begin_call(ctx, s))) return rc;
+    if ((rc = begin_call(ctx, n_tiles, (long long)n_out, s))) return rc;
     ScanParams P = make_params(ctx, d_in, n_in, lead, n_out, halo_left, threshold, base, prev_bit, 1);
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], s));
     CK(launch_scan(ctx, P, is_c64 != 0, 0u, (unsigned)n_tiles, s));
@@ -532,7 +526,7 @@ int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream)
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
     const long long n_tiles = tiles_for(ctx, ctx->last.n_out, ctx->last.lead);
     ctx->rerun_count++;
-    int rc = bump_epoch(ctx, s);
+    int rc = zero_cand_totals(ctx, ctx->last.n_out, s);
     if (rc) return rc;
     rc = launch_resolve(ctx, n_tiles, ctx->last.base, eob_in, s, true);
     if (rc) return rc;
@@ -552,7 +546,7 @@ int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int wor
     CK(cudaGetLastError());
     if (final_check) return ADSB_OK;
     const long long n_tiles = tiles_for(ctx, ctx->last.n_out, ctx->last.lead);
-    int rc = bump_epoch(ctx, s);
+    int rc = zero_cand_totals(ctx, ctx->last.n_out, s);
     if (rc) return rc;
     return launch_resolve(ctx, n_tiles, ctx->last.base, 0, s, true, true);   // no-ops unless hdr->carry_need
 }
@@ -627,7 +621,7 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
     const int prev_bit = (lead != 0) ? (0.0f >= threshold) : (ctx->prev_in0 >= threshold);
     const long long eob_in = ctx->prev_eob;
     cudaStream_t s = ctx->stream;
-    if ((rc = begin_call(ctx, s))) return rc;
+    if ((rc = begin_call(ctx, n_tiles, (long long)n_out, s))) return rc;
     ScanParams P = make_params(ctx, ctx->d_in, n_in, lead, n_out, 0, threshold, base, prev_bit, 1);
 
     // H2D in chunks on the copy stream; tiles are launched as soon as their samples (incl. the right
@@ -676,7 +670,7 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
     const int prev_bit = ctx->prev_in0 >= threshold;
     const long long eob_in = ctx->prev_eob;
     CK(cudaMemcpyAsync(ctx->d_in, in0, n_in * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = begin_call(ctx, s))) return rc;
+    if ((rc = begin_call(ctx, n_tiles, (long long)n_out, s))) return rc;
     ScanParams P = make_params(ctx, ctx->d_in, n_in, 0, n_out, 0, threshold, 0, prev_bit, 0);
     CK(launch_scan(ctx, P, false, 0u, (unsigned)n_tiles, s));
     if ((rc = launch_resolve(ctx, n_tiles, 0, eob_in, s))) return rc;

@@ -22,7 +22,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // flags in Header.flags
 constexpr unsigned kFlagRise = 1u, kFlagFall = 2u, kFlagCandOverflow = 4u, kFlagHalo = 8u,
-                   kFlagHitOverflow = 16u, kFlagSpin = 32u;
+                   kFlagHitOverflow = 16u;
 
 // == adsb_hit (include/adsb_b200.h)
 struct __align__(16) Rec {
@@ -44,9 +44,7 @@ struct Header {
     long long last_pulse;            // max pulse centre, window coordinates (-1: none)
     long long last_accept;           // max accepted centre, window coordinates (-1: none)
     unsigned flags;
-    unsigned tile_ticket;
-    unsigned chunk_ticket_g;         // gather kernel
-    unsigned chunk_ticket_c;         // compact kernel
+    unsigned pad0[3];
     float x_last;                    // x[n_out-1]  -> framer.py:87 prev_in0
     unsigned pad;
     long long first_cand;            // first candidate centre, window coordinates (-1: none)
@@ -81,6 +79,7 @@ struct ScanParams {
     Rec *cand;
     unsigned cand_cap;
     uint2 *tile_tab;       // per tile: (offset into cand, count)
+    unsigned *tile_chunk_tot;  // candidates per chunk of kThreads tiles (ordered offsets in gather_kernel)
     Header *hdr;
     const unsigned *crc_tab;   // 112 words: x^(111-i) mod g
 };

@@ -9,62 +9,22 @@
 
 namespace adsb {
 
-// ---- decoupled look-back over chunk aggregates (one warp) -------------------------------------------
-// status word: high 32 bits = (epoch << 2) | flag, low 32 bits = value; flag 1 = aggregate, 2 = inclusive.
-__device__ __forceinline__ unsigned long long pack_status(unsigned epoch, unsigned flag, unsigned v)
+// Ordered offsets without inter-block waiting: per-chunk totals are accumulated with fire-and-forget
+// atomics by the producer (K1 for tiles, chain_kernel for accepted candidates); a consumer block sums the
+// totals of the chunks before its own.
+__device__ __forceinline__ unsigned block_sum_before(const unsigned *tot, unsigned n, unsigned *scratch)
 {
-    return ((unsigned long long)((epoch << 2) | flag) << 32) | v;
-}
-
-__device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
-{
-    return __reduce_add_sync(kFull, v);
-}
-
-// called by all 32 lanes of one warp; returns the exclusive prefix of `agg` over chunks < idx
-__device__ unsigned lookback_exclusive(volatile unsigned long long *st, unsigned idx, unsigned agg,
-                                       unsigned epoch, unsigned *err_flags)
-{
-    const int lane = threadIdx.x & 31;
-    if (idx == 0) {
-        if (lane == 0) st[0] = pack_status(epoch, 2u, agg);
-        return 0u;
-    }
-    if (lane == 0) st[idx] = pack_status(epoch, 1u, agg);
-    unsigned excl = 0;
-    long long base = (long long)idx - 1;
-    unsigned spins = 0;
-    while (true) {
-        const long long t = base - lane;
-        unsigned long long s = 0;
-        bool ready = true, inc = true;
-        if (t >= 0) {
-            s = st[t];
-            const unsigned hi = (unsigned)(s >> 32);
-            ready = ((hi >> 2) == epoch) && ((hi & 3u) != 0u);
-            inc = ready && ((hi & 3u) == 2u);
-        }
-        const unsigned notready = __ballot_sync(kFull, !ready);
-        const unsigned usable = notready ? ((1u << (__ffs(notready) - 1)) - 1u) : kFull;
-        const unsigned incmask = __ballot_sync(kFull, inc) & usable;
-        if (incmask) {
-            const int first = __ffs(incmask) - 1;
-            excl += warp_sum_u32((lane <= first && t >= 0) ? (unsigned)s : 0u);
-            break;
-        }
-        if (usable == kFull) {
-            excl += warp_sum_u32((unsigned)s);
-            base -= 32;
-            continue;
-        }
-        if (++spins > (1u << 22)) {
-            if (lane == 0) atomicOr(err_flags, kFlagSpin);
-            break;
-        }
-        __nanosleep(40);
-    }
-    if (lane == 0) st[idx] = pack_status(epoch, 2u, excl + agg);
-    return excl;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned v = 0;
+    for (unsigned i = threadIdx.x; i < n; i += kThreads) v += tot[i];
+    v = __reduce_add_sync(kFull, v);
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    unsigned t = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; q++) t += scratch[q];
+    __syncthreads();
+    return t;
 }
 
 struct ResolveParams {
@@ -75,10 +35,9 @@ struct ResolveParams {
     Rec *hits;
     unsigned hit_cap;
     unsigned cand_cap;
-    volatile unsigned long long *status_g;
-    volatile unsigned long long *status_c;
+    unsigned *tile_chunk_tot;   // candidates per gather chunk (kTilesPerChunk tiles), filled by K1
+    unsigned *cand_chunk_tot;   // accepted candidates per compact chunk (kCandPerChunk), filled by chain_kernel
     Header *hdr;
-    unsigned epoch;
     long long base;             // records carry base + window index
     long long eob_in;           // incoming prev_eob_idx, window coordinates (framer.py:57,121)
     int blank;                  // 63 * sps (framer.py:165)
@@ -91,40 +50,47 @@ constexpr int kTilesPerChunk = kThreads;      // one tile per thread: enough blo
 __global__ void __launch_bounds__(kThreads) gather_kernel(const ResolveParams P)
 {
     __shared__ int scratch[16];
-    __shared__ unsigned s_chunk, s_excl;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ unsigned uscratch[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned n_chunks = (unsigned)((P.n_tiles + kTilesPerChunk - 1) / kTilesPerChunk);
-    while (true) {
-        if (tid == 0) s_chunk = atomicAdd(&P.hdr->chunk_ticket_g, 1u);
-        __syncthreads();
-        const unsigned chunk = s_chunk;
-        if (chunk >= n_chunks) break;
+    for (unsigned chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const long long t0 = (long long)chunk * kTilesPerChunk + tid;
         const uint2 tt = (t0 < P.n_tiles) ? P.tile_tab[t0] : make_uint2(0u, 0u);
         int total;
         const int off = block_excl_scan((int)tt.y, scratch, total);
-        if (wid == 0) {
-            unsigned e = lookback_exclusive(P.status_g, chunk, (unsigned)total, P.epoch, &P.hdr->flags);
-            if (lane == 0) s_excl = e;
-        }
-        __syncthreads();
+        const unsigned excl = block_sum_before(P.tile_chunk_tot, chunk, uscratch);
         // the last chunk knows the total: K1 only used hdr->n_cand as its overflow allocator
-        if (chunk == n_chunks - 1 && tid == 0) P.hdr->n_cand = (unsigned long long)s_excl + (unsigned long long)total;
-        const unsigned dst = s_excl + (unsigned)off;
-        // warp-cooperative copy: the 32 tiles of a warp one after the other, 16 bytes per lane
-        const unsigned any = __ballot_sync(kFull, tt.y != 0);
-        for (unsigned m = any; m; m &= m - 1) {
-            const int t = __ffs(m) - 1;
-            const unsigned src_t = __shfl_sync(kFull, tt.x, t);
-            const unsigned cnt_t = __shfl_sync(kFull, tt.y, t);
-            const unsigned dst_t = __shfl_sync(kFull, dst, t);
-            for (unsigned i = lane; i < 2 * cnt_t; i += 32) {
-                const unsigned r = i >> 1;
-                if (src_t + r < P.cand_cap && dst_t + r < P.cand_cap)
-                    reinterpret_cast<uint4 *>(P.ord + dst_t + r)[i & 1] = reinterpret_cast<const uint4 *>(P.cand + src_t + r)[i & 1];
-            }
+        if (chunk == n_chunks - 1 && tid == 0) P.hdr->n_cand = (unsigned long long)excl + (unsigned long long)total;
+        const unsigned dst = excl + (unsigned)off;
+        // warp-cooperative copy, flattened over the warp's 32 tiles so that every lane has an independent
+        // 16-byte load in flight each iteration (a per-tile loop serialises on the load latency)
+        __shared__ unsigned s_pre[kWarps][33], s_src[kWarps][32], s_dst[kWarps][32];
+        const int wid = tid >> 5;
+        unsigned inc = tt.y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
         }
-        __syncthreads();
+        s_pre[wid][lane + 1] = inc;                  // inclusive prefix of the warp's tile counts
+        if (lane == 0) s_pre[wid][0] = 0;
+        s_src[wid][lane] = tt.x;
+        s_dst[wid][lane] = dst;
+        __syncwarp();
+        const unsigned wtot = s_pre[wid][32];
+#pragma unroll 4
+        for (unsigned hidx = lane; hidx < 2 * wtot; hidx += 32) {
+            const unsigned r = hidx >> 1;
+            int t = 0;                               // tile with s_pre[t] <= r < s_pre[t+1]
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s_pre[wid][t + step] <= r) t += step;
+            const unsigned k = r - s_pre[wid][t];
+            const unsigned src = s_src[wid][t] + k, dd = s_dst[wid][t] + k;
+            if (src < P.cand_cap && dd < P.cand_cap)
+                reinterpret_cast<uint4 *>(P.ord + dd)[hidx & 1] = reinterpret_cast<const uint4 *>(P.cand + src)[hidx & 1];
+        }
+        __syncwarp();
     }
 }
 
@@ -133,6 +99,8 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const ResolveParams P)
 // eligible candidate whose predecessor is ineligible or more than 63 symbols behind starts a segment
 // and is always accepted; its thread then walks the segment greedily.  Accepted = flags bit 31.
 constexpr unsigned kAccepted = 0x80000000u;
+constexpr int kCandPerThread = 4;
+constexpr int kCandPerChunk = kThreads * kCandPerThread;   // candidates per compact_kernel block iteration
 
 __global__ void __launch_bounds__(kThreads) chain_kernel(const ResolveParams P)
 {
@@ -141,36 +109,48 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const ResolveParams P)
     const long long M = (long long)(m64 < P.cand_cap ? m64 : P.cand_cap);
     const long long e_in = P.dev_carry ? P.hdr->carry_ein : P.base + P.eob_in;
     const long long D = P.blank;
+    const int lane = threadIdx.x & 31;
     // every record's accepted bit is assigned exactly once per launch (by the record's own thread when
     // it is ineligible, otherwise by the head of its segment), so the kernel can be re-run with
-    // another eob_in (multi-GPU carry fix-up)
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long c = P.ord[i].idx;
-        if (i == 0) P.hdr->first_cand = c - P.base;
-        if (c <= e_in) {                            // framer.py:121: still blanked by the incoming state
-            P.ord[i].flags &= ~kAccepted;
-            continue;
-        }
-        bool head = (i == 0);
-        if (!head) {
-            const long long cp = P.ord[i - 1].idx;
-            head = (cp <= e_in) || (c - cp > D);
-        }
-        if (!head) continue;
-        long long last = c, prev = c;
-        P.ord[i].flags |= kAccepted;
-        for (long long j = i + 1; j < M; j++) {
-            const long long cj = P.ord[j].idx;
-            if (cj - prev > D) break;               // next segment (its own head handles it)
-            prev = cj;
-            if (cj > last + D) {                    // framer.py:121 with prev_eob_idx = last + 63*sps
-                P.ord[j].flags |= kAccepted;
-                last = cj;
+    // another eob_in (multi-GPU carry fix-up).  Accepted candidates are counted per compact chunk: a warp's
+    // 32 consecutive candidates share one chunk, so the count goes out as one atomic per warp.
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const long long my_chunk = i / kCandPerChunk;
+        unsigned local = 0;
+        if (i < M) {
+            const long long c = P.ord[i].idx;
+            if (i == 0) P.hdr->first_cand = c - P.base;
+            if (c <= e_in) {                            // framer.py:121: still blanked by the incoming state
+                P.ord[i].flags &= ~kAccepted;
             } else {
-                P.ord[j].flags &= ~kAccepted;
+                bool head = (i == 0);
+                if (!head) {
+                    const long long cp = P.ord[i - 1].idx;
+                    head = (cp <= e_in) || (c - cp > D);
+                }
+                if (head) {
+                    long long last = c, prev = c;
+                    P.ord[i].flags |= kAccepted;
+                    local++;
+                    for (long long j = i + 1; j < M; j++) {
+                        const long long cj = P.ord[j].idx;
+                        if (cj - prev > D) break;               // next segment (its own head handles it)
+                        prev = cj;
+                        if (cj > last + D) {                    // framer.py:121 with prev_eob_idx = last + 63*sps
+                            P.ord[j].flags |= kAccepted;
+                            last = cj;
+                            if (j / kCandPerChunk == my_chunk) local++;
+                            else atomicAdd(&P.cand_chunk_tot[j / kCandPerChunk], 1u);
+                        } else {
+                            P.ord[j].flags &= ~kAccepted;
+                        }
+                    }
+                }
             }
         }
+        const unsigned wsum = __reduce_add_sync(kFull, local);
+        if (lane == 0 && wsum) atomicAdd(&P.cand_chunk_tot[(base + (threadIdx.x & ~31)) / kCandPerChunk], wsum);
     }
 }
 
@@ -182,27 +162,20 @@ __global__ void reset_resolve_kernel(Header *h, int dev_carry)
     h->n_demod = 0;
     h->n_crc = 0;
     h->last_accept = -1;
-    h->chunk_ticket_c = 0;
 }
 
 // ---- compact: accepted candidates -> ordered hit list ------------------------------------------------
-constexpr int kCandPerThread = 4;
-constexpr int kCandPerChunk = kThreads * kCandPerThread;   // big chunks keep the look-back chain short
 
 __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P)
 {
     __shared__ int scratch[16];
-    __shared__ unsigned s_chunk, s_excl;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ unsigned uscratch[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31;
     if (P.dev_carry && !P.hdr->carry_need) return;
     const unsigned long long m64 = P.hdr->n_cand;
     const long long M = (long long)(m64 < P.cand_cap ? m64 : P.cand_cap);
     const unsigned n_chunks = (unsigned)((M + kCandPerChunk - 1) / kCandPerChunk);
-    while (true) {
-        if (tid == 0) s_chunk = atomicAdd(&P.hdr->chunk_ticket_c, 1u);
-        __syncthreads();
-        const unsigned chunk = s_chunk;
-        if (chunk >= n_chunks) break;
+    for (unsigned chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const long long i0 = (long long)chunk * kCandPerChunk + (long long)tid * kCandPerThread;
         Rec r[kCandPerThread];
         int acc = 0;
@@ -226,10 +199,7 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
         }
         int total;
         const int off = block_excl_scan(acc, scratch, total);
-        if (wid == 0) {
-            unsigned e = lookback_exclusive(P.status_c, chunk, (unsigned)total, P.epoch, &P.hdr->flags);
-            if (lane == 0) s_excl = e;
-        }
+        const unsigned excl = block_sum_before(P.cand_chunk_tot, chunk, uscratch);
         // block counters
         n_demod = __reduce_add_sync(kFull, n_demod);
         n_crc = __reduce_add_sync(kFull, n_crc);
@@ -243,8 +213,7 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
             if (n_crc) atomicAdd(&P.hdr->n_crc, (unsigned long long)n_crc);
             if (mx >= 0) atomicMax(&P.hdr->last_accept, mx - P.base);
         }
-        __syncthreads();
-        unsigned dst = s_excl + (unsigned)off;
+        unsigned dst = excl + (unsigned)off;
 #pragma unroll
         for (int q = 0; q < kCandPerThread; q++) {
             if (r[q].flags & kAccepted) {
@@ -261,7 +230,6 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const ResolveParams P
             }
         }
         if (tid == 0 && total) atomicAdd(&P.hdr->n_hits, (unsigned long long)total);
-        __syncthreads();
     }
 }
 

@@ -736,6 +736,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         if (n_cand > kTileSlots)
             off = (unsigned)P.n_tiles_total * kTileSlots + (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
         P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
+        if (n_cand > 0) atomicAdd(&P.tile_chunk_tot[tile / kThreads], (unsigned)n_cand);   // gather_kernel's chunks
         sm.scratch[kScrOff] = (int)off;
         sm.scratch[kScrNCand] = n_cand;
         sm.scratch[kScrFast] = fast ? 1 : 0;
