@@ -14,6 +14,9 @@
 
 namespace adsb {
 
+#ifndef ADSB_MIN_CTAS_BIG
+#define ADSB_MIN_CTAS_BIG 4  // same for the 8192-sample tile kernels (8 Msps and unspecialised rates)
+#endif
 #ifndef ADSB_LMAX2
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
@@ -820,7 +823,7 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
 
 // ---- the kernel: one CTA (8 warps) per tile, phases in sequence ---------------------------------------------
 template <int SPS, bool C64>
-__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : 2) scan_slice_kernel(const ScanParams P)
+__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) scan_slice_kernel(const ScanParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileSmem sm = carve(smem_raw, Geo<SPS>::T, SPS ? Geo<SPS>::RH : P.rh);
