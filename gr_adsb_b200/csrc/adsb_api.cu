@@ -83,6 +83,7 @@ struct adsb_ctx {
     } last;
     adsb_counters counters;
     int profile;
+    unsigned prefetch_tiles;     // L2 prefetch distance of the scan kernel, in tiles
     unsigned rerun_count;
     cudaEvent_t pev[3];
     char err[256];
@@ -194,10 +195,7 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     P.tile_chunk_tot = c->d_tile_chunk_tot;
     P.hdr = c->d_hdr;
     P.crc_tab = c->d_crc;
-    {
-        const char *e = getenv("ADSB_PREFETCH_TILES");
-        P.prefetch_tiles = e ? (unsigned)atoi(e) : (unsigned)(c->num_sms * 2);
-    }
+    P.prefetch_tiles = c->prefetch_tiles;
     // tiles t with: t >= 1, (t+1)*T + rh <= n_arr, t*T + lead >= own_lo, (t+1)*T + lead <= own_hi
     {
         const long long T = c->T;
@@ -387,6 +385,10 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->prev_in0 = 0.0f;
     ctx->prev_eob = -1;
     ctx->num_sms = prop.multiProcessorCount;
+    {
+        const char *e = getenv("ADSB_PREFETCH_TILES");      // tuning knob; default: two tiles per SM ahead
+        ctx->prefetch_tiles = e ? (unsigned)atoi(e) : (unsigned)(ctx->num_sms * 2);
+    }
     ctx->err[0] = 0;
 
     auto die = [&](int code, const char *what, cudaError_t e) {
