@@ -125,3 +125,68 @@ class demod(gr.sync_block, _DeviceBlock):
                 self.message_port_pub(port, pmt.cons(meta, pmt.to_pmt(self.bits)))
         out0[:] = in0
         return len(output_items[0])
+
+
+class burst(gr.sync_block, _DeviceBlock):
+    """framer + demod in ONE block and one device round trip per work() call.
+
+    Emits exactly what the chain `framer -> demod` emits when the scheduler runs the two in lock step:
+    the same "burst" tags on the output stream and the same PDUs on "demodulated" (bursts that do not
+    end inside the buffer are dropped, demod.py:82,130-133).  With `complex_input=True` the block also
+    absorbs `blocks.complex_to_mag_squared` (examples/adsb_rx.py:180) and takes the SDR's complex64
+    stream directly; the output stream is then |IQ|^2 of the input, as the removed block produced.
+    """
+
+    def __init__(self, fs, threshold, complex_input=False, device=0):
+        in_t = np.complex64 if complex_input else np.float32
+        gr.sync_block.__init__(self, name="ADS-B Burst (framer+demod)", in_sig=[in_t], out_sig=[np.float32])
+        self.fs = fs
+        assert self.fs % SYMBOL_RATE == 0, "integer number of samples per symbol required"
+        self.sps = int(fs // SYMBOL_RATE)
+        assert self.sps >= 2 and self.sps % 2 == 0
+        self.threshold = threshold
+        self.complex_input = bool(complex_input)
+        self.device = device
+        self.N_hist = NUM_PREAMBLE_BITS * self.sps
+        self.set_history(self.N_hist)
+        self.set_tag_propagation_policy(gr.TPP_ONE_TO_ONE)
+        self.message_port_register_out(pmt.to_pmt("demodulated"))
+        self.start_timestamp = (datetime.datetime.now(datetime.timezone.utc)
+                                - datetime.datetime(1970, 1, 1, tzinfo=datetime.timezone.utc)).total_seconds()
+        self._ctx_for(_DEFAULT_MAX_ITEMS)
+
+    @property
+    def prev_in0(self):
+        return self._ctx.get_state()[0]
+
+    @property
+    def prev_eob_idx(self):
+        return self._ctx.get_state()[1]
+
+    def set_threshold(self, threshold):
+        self.threshold = threshold
+
+    def work(self, input_items, output_items):
+        in0 = input_items[0]
+        out0 = output_items[0]
+        N = len(out0)
+        ctx = self._ctx_for(len(in0))
+        hits = ctx.burst_work(in0, n_out=N, lead=0, threshold=self.threshold)
+        if len(hits):
+            origin = self.nitems_written(0) - (self.N_hist - 1)
+            key, src, port = pmt.to_pmt("burst"), pmt.to_pmt("framer"), pmt.to_pmt("demodulated")
+            bits = _native.unpack_bits(hits)
+            for k in range(len(hits)):
+                off = origin + int(hits["idx"][k])
+                snr = float(hits["snr"][k])
+                self.add_item_tag(0, off, key, pmt.to_pmt(("SOB", snr)), src)
+                if hits["flags"][k] & _native.HIT_DEMOD_VALID:
+                    meta = pmt.to_pmt({"timestamp": self.start_timestamp + off / self.fs, "snr": snr})
+                    self.message_port_pub(port, pmt.cons(meta, pmt.to_pmt(bits[k].copy())))
+        tail = in0[self.N_hist - 1:]
+        if self.complex_input:
+            v = np.ascontiguousarray(tail).view(np.float32).reshape(-1, 2)
+            out0[:] = v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]
+        else:
+            out0[:] = tail
+        return N
