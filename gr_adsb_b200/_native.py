@@ -226,19 +226,19 @@ class Context(object):
         return out.value
 
     def burst_finish(self, fetch_hits=True, cap=None):
+        """Counters of the latest resolve (dict) and, optionally, the hit records (structured array)."""
         c = Counters()
         n = C.c_size_t(0)
         if not fetch_hits:
             self._check(lib().adsb_burst_finish(self._h, C.byref(c), None, 0, C.byref(n)))
             return c.as_dict(), None
         cap = cap or 1 << 16
-        while True:
-            hits = np.zeros(cap, HIT_DTYPE)
-            rc = lib().adsb_burst_finish(self._h, C.byref(c), _ptr(hits), cap, C.byref(n))
-            if rc == E_CAPACITY:
-                raise AdsbError(rc, "burst_finish: pass cap >= %d" % n.value)
-            self._check(rc)
-            return c.as_dict(), hits[:n.value]
+        hits = np.zeros(cap, HIT_DTYPE)
+        rc = lib().adsb_burst_finish(self._h, C.byref(c), _ptr(hits), cap, C.byref(n))
+        if rc == E_CAPACITY:
+            raise AdsbError(rc, "burst_finish: pass cap >= %d" % n.value)
+        self._check(rc)
+        return c.as_dict(), hits[:n.value]
 
 
 def _profile_methods():
