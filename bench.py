@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sps", type=int, default=SPS, help="samples per symbol (secondary workloads; default 2)")
     ap.add_argument("--density", type=float, default=DENSITY, help="bursts per sample (default 5e-3 = 10k/s at 2 Msps)")
+    ap.add_argument("--fec", action="store_true", help="enable the conservative error correction (decoder.py error_corr)")
     ap.add_argument("--f32", action="store_true", help="feed float32 |IQ|^2 instead of complex64 (BASELINE configs[0] layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -219,6 +220,8 @@ def main():
         del buf
         buf = work_buf
     ctx = g.Context(SPS, geo["n_in"], device=local)
+    if args.fec:
+        ctx.set_error_correction(g.FEC_CONSERVATIVE)
     stream = torch.cuda.Stream(device=dev)      # a real (non-NULL) stream: kernels and timing events share it
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
@@ -274,7 +277,8 @@ def main():
     if world > 1 and counters["carry_unstable"]:
         raise RuntimeError("blanking carry did not settle in one round on rank %d (%d steps): results would differ "
                            "from the whole-buffer oracle" % (rank, counters["carry_unstable"]))
-    stats = torch.tensor([counters["n_hits"], counters["n_crc_ok"], counters["n_demod"], counters["n_candidates"]],
+    stats = torch.tensor([counters["n_hits"], counters["n_crc_ok"] + counters["n_fec_fixed"], counters["n_demod"],
+                          counters["n_candidates"]],
                          dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(stats)
@@ -310,9 +314,11 @@ def main():
             "hits_per_step": n_hits, "candidates_per_step": n_cand, "crc_pass_per_step": n_crc,
             "crc_pass_bursts_per_s": n_crc / (ms_per_step * 1e-3),
             "roofline": roofline}
-    if args.sps != 2 or args.density != 5e-3 or args.f32:
+    if args.sps != 2 or args.density != 5e-3 or args.f32 or args.fec:
         line["config"]["workload"] = ("secondary workload (not the headline): %d Msps %s, %.3g bursts/sample, threshold %.3g, "
                                       "whole-buffer semantics" % (SPS, "float32 |IQ|^2" if args.f32 else "complex64 IQ", DENSITY, THRESHOLD))
+    if args.fec:
+        line["error_correction"] = {"mode": "Conservative (decoder.py:738-763)", "fixed_per_step_rank0": counters["n_fec_fixed"]}
     if world > 1:
         line["carry"] = {"allgather_rounds_per_step": rounds[0] / args.steps, "host_syncs_per_step": 0,
                          "unsettled_steps": counters["carry_unstable"]}

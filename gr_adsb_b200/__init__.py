@@ -4,7 +4,8 @@
 (python/adsb/__init__.py:24-25); `burst` is the two fused into one block (optionally taking complex64 IQ); `Context` is the raw ctypes handle onto `include/adsb_b200.h`.
 """
 from ._native import Context, AdsbError, HIT_DTYPE, unpack_bits, build, lib  # noqa: F401
-from ._native import HIT_DEMOD_VALID, HIT_CRC_OK, HIT_LATE_TAG, CARRY_USED_ON_DEVICE  # noqa: F401
+from ._native import HIT_DEMOD_VALID, HIT_CRC_OK, HIT_LATE_TAG, HIT_FEC_FIXED, CARRY_USED_ON_DEVICE  # noqa: F401
+from ._native import FEC_NONE, FEC_CONSERVATIVE  # noqa: F401
 
 
 def __getattr__(name):

@@ -18,6 +18,8 @@ E_CAPACITY = -4
 HIT_DEMOD_VALID = 0x1
 HIT_CRC_OK = 0x2
 HIT_LATE_TAG = 0x4
+HIT_FEC_FIXED = 0x8
+FEC_NONE, FEC_CONSERVATIVE = 0, 1
 CARRY_USED_ON_DEVICE = -(1 << 63)
 
 HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
@@ -28,7 +30,7 @@ class Counters(C.Structure):
     _fields_ = [("n_samples", C.c_uint64), ("n_candidates", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_demod", C.c_uint64), ("n_crc_ok", C.c_uint64), ("last_pulse", C.c_int64),
                 ("last_accept", C.c_int64), ("first_candidate", C.c_int64),
-                ("carry_unstable", C.c_uint32), ("reserved", C.c_uint32),
+                ("carry_unstable", C.c_uint32), ("n_fec_fixed", C.c_uint32),
                 ("any_rise", C.c_uint32), ("any_fall", C.c_uint32)]
 
     def as_dict(self):
@@ -58,7 +60,7 @@ EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_creat
            "adsb_last_error", "adsb_reset_state", "adsb_get_state", "adsb_set_state", "adsb_get_counters",
            "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish",
            "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
-           "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev"]
+           "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev", "adsb_set_error_correction"]
 
 
 def lib():
@@ -85,6 +87,8 @@ def lib():
     L.adsb_get_state.argtypes = [vp, C.POINTER(f32), C.POINTER(i64)]
     L.adsb_set_state.restype = i32
     L.adsb_set_state.argtypes = [vp, f32, i64]
+    L.adsb_set_error_correction.restype = i32
+    L.adsb_set_error_correction.argtypes = [vp, i32]
     L.adsb_get_counters.restype = i32
     L.adsb_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.adsb_framer_work.restype = i32
@@ -162,6 +166,10 @@ class Context(object):
 
     def set_state(self, prev_in0, prev_eob_idx):
         self._check(lib().adsb_set_state(self._h, float(prev_in0), int(prev_eob_idx)))
+
+    def set_error_correction(self, mode):
+        """FEC_NONE or FEC_CONSERVATIVE (decoder.py:765-780), for the fused entry points."""
+        self._check(lib().adsb_set_error_correction(self._h, int(mode)))
 
     def counters(self):
         c = Counters()

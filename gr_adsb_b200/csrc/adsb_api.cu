@@ -84,6 +84,9 @@ struct adsb_ctx {
     adsb_counters counters;
     int profile;
     unsigned prefetch_tiles;     // L2 prefetch distance of the scan kernel, in tiles
+    int fec_mode;                // ADSB_FEC_*
+    unsigned *d_fec_t25, *d_fec_keys;
+    unsigned short *d_fec_fix;
     unsigned rerun_count;
     cudaEvent_t pev[3];
     char err[256];
@@ -107,6 +110,53 @@ int fail(adsb_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
         cudaError_t e_ = (call);                                          \
         if (e_ != cudaSuccess) return fail(ctx, ADSB_E_CUDA, #call, e_);  \
     } while (0)
+
+// decoder.compute_crc_2 (decoder.py:716-736) on a 112-bit pattern: reduce positions 0..86, return bits 87..111
+unsigned residual25(const unsigned char *bits112)
+{
+    unsigned char d[kMsgBits];
+    memcpy(d, bits112, kMsgBits);
+    static const unsigned char poly[25] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1};
+    for (int i = 0; i < kMsgBits - 25; i++)
+        if (d[i])
+            for (int j = 0; j < 25; j++) d[i + j] ^= poly[j];
+    unsigned v = 0;
+    for (int i = kMsgBits - 25; i < kMsgBits; i++) v = (v << 1) | d[i];
+    return v;
+}
+
+// tables of the conservative error correction (decoder.py:304-323): unit-vector residuals, and the residuals
+// of every 1-bit / 2-contiguous-bit pattern sorted ascending with the bits to flip
+void fec_tables(unsigned *t25, unsigned *keys, unsigned short *fix)
+{
+    unsigned char z[kMsgBits];
+    for (int i = 0; i < kMsgBits; i++) {
+        memset(z, 0, sizeof(z));
+        z[i] = 1;
+        t25[i] = residual25(z);
+    }
+    int n = 0;
+    for (int burst = 1; burst <= 2; burst++)
+        for (int i = 0; i + burst <= kMsgBits; i++) {
+            unsigned k = 0;
+            for (int q = 0; q < burst; q++) k ^= t25[i + q];
+            keys[n] = k;
+            fix[n] = (unsigned short)(i | (burst << 8));
+            n++;
+        }
+    for (int a = 1; a < n; a++) {           // insertion sort by key (223 entries)
+        const unsigned k = keys[a];
+        const unsigned short f = fix[a];
+        int b = a - 1;
+        while (b >= 0 && keys[b] > k) {
+            keys[b + 1] = keys[b];
+            fix[b + 1] = fix[b];
+            b--;
+        }
+        keys[b + 1] = k;
+        fix[b + 1] = f;
+    }
+}
 
 void crc_table(unsigned *t)
 {
@@ -246,6 +296,16 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
         gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
     chain_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
     compact_kernel<<<cblocks, kThreads, 0, s>>>(R);
+    if (ctx->fec_mode == ADSB_FEC_CONSERVATIVE) {
+        FecParams F;
+        F.hits = ctx->d_hits;
+        F.hdr = ctx->d_hdr;
+        F.hit_cap = ctx->hit_cap;
+        F.t25 = ctx->d_fec_t25;
+        F.keys = ctx->d_fec_keys;
+        F.fix = ctx->d_fec_fix;
+        fec_kernel<<<cap_blocks, kThreads, 0, s>>>(F);
+    }
     CK(cudaGetLastError());
     return ADSB_OK;
 }
@@ -349,6 +409,9 @@ void adsb_destroy(adsb_ctx *ctx)
     cudaFree(ctx->d_cand_chunk_tot);
     cudaFree(ctx->d_hdr);
     cudaFree(ctx->d_crc);
+    cudaFree(ctx->d_fec_t25);
+    cudaFree(ctx->d_fec_keys);
+    cudaFree(ctx->d_fec_fix);
     cudaFree(ctx->d_sob);
     cudaFree(ctx->d_bits);
     cudaFree(ctx->d_valid);
@@ -429,6 +492,9 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ALLOC(ctx->d_cand_chunk_tot, ctx->cand_chunk_n * sizeof(unsigned));
     ALLOC(ctx->d_hdr, sizeof(Header));
     ALLOC(ctx->d_crc, kMsgBits * sizeof(unsigned));
+    ALLOC(ctx->d_fec_t25, kMsgBits * sizeof(unsigned));
+    ALLOC(ctx->d_fec_keys, kFecPatterns * sizeof(unsigned));
+    ALLOC(ctx->d_fec_fix, kFecPatterns * sizeof(unsigned short));
     ALLOC(ctx->d_sob, ctx->tag_cap * sizeof(long long));
     ALLOC(ctx->d_bits, ctx->tag_cap * kMsgBits);
     ALLOC(ctx->d_valid, ctx->tag_cap);
@@ -437,6 +503,15 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     unsigned tab[kMsgBits];
     crc_table(tab);
     if ((e = cudaMemcpy(ctx->d_crc, tab, sizeof(tab), cudaMemcpyHostToDevice)) != cudaSuccess) return die(ADSB_E_CUDA, "crc table", e);
+    {
+        unsigned t25[kMsgBits], keys[kFecPatterns];
+        unsigned short fix[kFecPatterns];
+        fec_tables(t25, keys, fix);
+        if ((e = cudaMemcpy(ctx->d_fec_t25, t25, sizeof(t25), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(ctx->d_fec_keys, keys, sizeof(keys), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(ctx->d_fec_fix, fix, sizeof(fix), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return die(ADSB_E_CUDA, "fec tables", e);
+    }
     *out = ctx;
     return ADSB_OK;
 }
@@ -462,6 +537,13 @@ int adsb_set_state(adsb_ctx *ctx, float prev_in0, int64_t prev_eob_idx)
     if (!ctx) return ADSB_E_INVAL;
     ctx->prev_in0 = prev_in0;
     ctx->prev_eob = prev_eob_idx;
+    return ADSB_OK;
+}
+
+int adsb_set_error_correction(adsb_ctx *ctx, int mode)
+{
+    if (!ctx || (mode != ADSB_FEC_NONE && mode != ADSB_FEC_CONSERVATIVE)) return ADSB_E_INVAL;
+    ctx->fec_mode = mode;
     return ADSB_OK;
 }
 
@@ -589,6 +671,7 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
     c.last_accept = h.last_accept;
     c.first_candidate = h.first_cand;
     c.carry_unstable = h.carry_unstable;
+    c.n_fec_fixed = h.n_fec;
     c.any_rise = (h.flags & kFlagRise) ? 1u : 0u;
     c.any_fall = (h.flags & kFlagFall) ? 1u : 0u;
     if (counters) *counters = c;

@@ -33,7 +33,7 @@ struct __align__(16) Rec {
 };
 static_assert(sizeof(Rec) == 32, "record must stay 32 bytes");
 
-constexpr unsigned kHitDemodValid = 1u, kHitCrcOk = 2u, kHitLate = 4u;
+constexpr unsigned kHitDemodValid = 1u, kHitCrcOk = 2u, kHitLate = 4u, kHitFecFixed = 8u;
 constexpr long long kCarryNone = -(1LL << 62);   // "no blanking state" / "no candidate" in the carry exchange
 
 struct Header {
@@ -44,7 +44,8 @@ struct Header {
     long long last_pulse;            // max pulse centre, window coordinates (-1: none)
     long long last_accept;           // max accepted centre, window coordinates (-1: none)
     unsigned flags;
-    unsigned pad0[3];
+    unsigned n_fec;                  // hits repaired by the conservative error correction
+    unsigned pad0[2];
     float x_last;                    // x[n_out-1]  -> framer.py:87 prev_in0
     unsigned pad;
     long long first_cand;            // first candidate centre, window coordinates (-1: none)

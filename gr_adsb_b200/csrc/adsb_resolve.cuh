@@ -162,6 +162,7 @@ __global__ void reset_resolve_kernel(Header *h, int dev_carry)
     h->n_demod = 0;
     h->n_crc = 0;
     h->last_accept = -1;
+    h->n_fec = 0;
 }
 
 // ---- compact: accepted candidates -> ordered hit list ------------------------------------------------
@@ -261,6 +262,62 @@ __global__ void carry_plan_kernel(Header *h, const long long *gathered, int worl
         h->carry_ein = my_e;
         h->carry_used = my_e;       // where no re-run is needed the result is the same under either value
     }
+}
+
+// ---- "Conservative" error correction (decoder.py:304-323, 738-763): one thread per hit -----------------------
+// A hit that was demodulated, fails the parity check and carries DF 17..19 gets its 25-bit residual
+// (decoder.compute_crc_2: the division stops one step early) looked up among the residuals of all 1-bit and
+// 2-contiguous-bit error patterns; a match flips those bits and the message counts as passed.
+constexpr int kFecPatterns = 112 + 111;
+
+struct FecParams {
+    Rec *hits;
+    Header *hdr;
+    unsigned hit_cap;
+    const unsigned *t25;            // [112] residual25 of the unit vector at bit i
+    const unsigned *keys;           // [kFecPatterns] residuals of the error patterns, ascending
+    const unsigned short *fix;      // [kFecPatterns] first bit | (length << 8), same order
+};
+
+__global__ void __launch_bounds__(kThreads) fec_kernel(const FecParams P)
+{
+    const unsigned long long n64 = P.hdr->n_hits;
+    const unsigned n = (unsigned)(n64 < P.hit_cap ? n64 : P.hit_cap);
+    unsigned fixed = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned flags = P.hits[i].flags;
+        if (!(flags & kHitDemodValid) || (flags & kHitCrcOk)) continue;
+        unsigned w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = P.hits[i].bits[j];
+        // message bit k sits in byte k/8 (little-endian words), bit 7 - k%8
+        const unsigned df = (w[0] & 0xffu) >> 3;
+        if (df < 17 || df > 19) continue;                       // payload_length never set (decoder.py:667-670)
+        unsigned r = 0;
+        for (int k = 0; k < kMsgBits; k++) {
+            const unsigned bit = (w[k >> 5] >> (8 * ((k >> 3) & 3) + 7 - (k & 7))) & 1u;
+            r ^= bit ? P.t25[k] : 0u;
+        }
+        int lo = 0, hi = kFecPatterns - 1, found = -1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const unsigned key = P.keys[mid];
+            if (key == r) { found = mid; break; }
+            if (key < r) lo = mid + 1; else hi = mid - 1;
+        }
+        if (found < 0) continue;
+        const unsigned f = P.fix[found];
+        for (unsigned q = 0; q < (f >> 8); q++) {
+            const unsigned k = (f & 0xffu) + q;
+            w[k >> 5] ^= 1u << (8 * ((k >> 3) & 3) + 7 - (k & 7));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) P.hits[i].bits[j] = w[j];
+        P.hits[i].flags = flags | kHitCrcOk | kHitFecFixed;
+        fixed++;
+    }
+    fixed = __reduce_add_sync(kFull, fixed);
+    if ((threadIdx.x & 31) == 0 && fixed) atomicAdd(&P.hdr->n_fec, fixed);
 }
 
 // ---- stand-alone demod (demod.py:75-95) ----------------------------------------------------------------

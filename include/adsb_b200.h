@@ -46,6 +46,7 @@ enum {
 /* adsb_hit.flags */
 #define ADSB_HIT_DEMOD_VALID 0x1u /* burst lies fully inside the buffer: bits[] valid (demod.py:82)            */
 #define ADSB_HIT_CRC_OK      0x2u /* DF in {17,18,19} and PI == CRC-24(bits[0:88]) (decoder.py:667-685)         */
+#define ADSB_HIT_FEC_FIXED   0x8u /* parity restored by the conservative error correction (then CRC_OK is set too)  */
 #define ADSB_HIT_LATE_TAG    0x4u /* window index < 8*sps-1: tag lands on an item of the previous call (A.9) */
 
 /* One detected burst.  `bits` holds the 112 demodulated bits packed MSB first (numpy.packbits
@@ -68,7 +69,7 @@ typedef struct adsb_counters {
     int64_t last_accept;    /* centre of the last hit, window coordinates, -1 if none       */
     int64_t first_candidate;/* centre of the first candidate, window coordinates, -1 if none */
     uint32_t carry_unstable; /* device-side carry rounds whose final check still wanted a fix-up  */
-    uint32_t reserved;
+    uint32_t n_fec_fixed;    /* hits with ADSB_HIT_FEC_FIXED (not included in n_crc_ok)            */
     uint32_t any_rise;      /* framer.py:95 guard inputs                                   */
     uint32_t any_fall;
 } adsb_counters;
@@ -90,6 +91,14 @@ int adsb_reset_state(adsb_ctx *ctx);
 int adsb_get_state(const adsb_ctx *ctx, float *prev_in0, int64_t *prev_eob_idx);
 int adsb_set_state(adsb_ctx *ctx, float prev_in0, int64_t prev_eob_idx);
 int adsb_get_counters(const adsb_ctx *ctx, adsb_counters *out);
+
+/* decoder.py:765-780 error_corr: ADSB_FEC_NONE (default, "None") or ADSB_FEC_CONSERVATIVE ("Conservative":
+ * decoder.py:304-323,738-763 -- hits that fail the parity check with DF 17..19 whose 25-bit residual matches a
+ * 1-bit or 2-contiguous-bit error pattern get those bits flipped, ADSB_HIT_CRC_OK | ADSB_HIT_FEC_FIXED set).
+ * Applies to the fused entry points (adsb_burst_work*); the block API leaves correction to adsb.decoder. */
+#define ADSB_FEC_NONE 0
+#define ADSB_FEC_CONSERVATIVE 1
+int adsb_set_error_correction(adsb_ctx *ctx, int mode);
 
 /* framer.work(): in0[n_in] is float32 |IQ|^2 with n_in == n_out + 8*sps - 1 (GNU Radio history).
  * Writes the pulse-centre window index and SNR of every "burst" tag, ascending; the caller adds

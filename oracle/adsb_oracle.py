@@ -174,3 +174,56 @@ def crc_pass(bits112):
     if df not in (17, 18, 19):
         return 0
     return int(np.array_equal(compute_crc(b[:88]), b[88:112]))
+
+
+# --- Conservative error correction (decoder.py:304-323, 716-763, 765-780) -------------
+def residual25(bits):
+    """decoder.compute_crc_2 (decoder.py:716-736): long division that stops one step early and returns the
+    25-bit window bits[len-25:len] as an integer -- the quantity the reference's syndrome table is keyed by."""
+    d = np.asarray(bits, dtype=np.int64).copy()
+    n = len(d) - 25
+    for i in range(n):
+        if d[i]:
+            d[i:i + 25] ^= CRC_POLY_BITS
+    v = 0
+    for b in d[n:n + 25]:
+        v = (v << 1) | int(b)
+    return v
+
+
+def fec_table(payload_length=112):
+    """decoder.compute_crc_syndromes_for_contiguous_bursts (decoder.py:304-323) for bursts of 1 and 2 bits:
+    {residual25(error pattern): [bit positions]}."""
+    lut = {}
+    for burst in (1, 2):
+        for i in range(payload_length - burst + 1):
+            z = np.zeros(payload_length, dtype=np.int64)
+            z[i:i + burst] = 1
+            key = residual25(z)
+            assert key not in lut, "FEC syndrome collision"         # decoder.py:319-321
+            lut[key] = list(range(i, i + burst))
+    return lut
+
+
+_FEC112 = None
+
+
+def conservative_fix(bits112):
+    """What decoder.decode_packet does up to the parity verdict with msg_filter="Extended Squitter Only",
+    error_corr="Conservative" (decoder.py:341-344): returns (parity_passed, fixed, bits_after)."""
+    global _FEC112
+    b = np.array(bits112, dtype=np.uint8).copy()
+    if crc_pass(b):
+        return 1, 0, b
+    df = int("".join(str(int(v)) for v in b[:5]), 2)
+    if df not in (17, 18, 19):            # check_parity never set payload_length (decoder.py:667-670,739-740)
+        return 0, 0, b
+    if _FEC112 is None:
+        _FEC112 = fec_table(112)
+    pos = _FEC112.get(residual25(b))
+    if pos is None:
+        return 0, 0, b
+    for p in pos:
+        b[p] ^= 1
+    ok = int(residual25(b) == 0)          # decoder.py:756-758
+    return ok, ok, b

@@ -146,3 +146,23 @@ def compute_crc(bits, dec=None):
     """reference decoder.compute_crc(bits, crc_poly) (decoder.py:693-715) -> 24 bits."""
     dec = dec or new_decoder()
     return np.array(dec.compute_crc(np.array(bits, dtype=int), dec.crc_poly), dtype=np.uint8)
+
+
+def conservative_fix(bits112, dec=None):
+    """The reference decoder's own steps of decode_packet (decoder.py:337-344) with error_corr="Conservative":
+    returns (parity_passed, bits_after)."""
+    dec = dec or new_decoder(error_corr="Conservative")
+    import logging
+    logging.disable(logging.CRITICAL)
+    try:
+        dec.reset()
+        dec.bits = np.array(bits112, dtype=np.uint8).copy()
+        dec.snr = 0.0
+        dec.datetime = ""
+        dec.decode_header()
+        passed = dec.check_parity()
+        if passed == 0:
+            passed = dec.correct_errors()
+        return int(bool(passed)), np.array(dec.bits, dtype=np.uint8)
+    finally:
+        logging.disable(logging.NOTSET)

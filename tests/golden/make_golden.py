@@ -152,5 +152,45 @@ def main():
     emit("sps2_dense_wide", synth.mag2(d["iq"]), 2e6, 0.01, [None, 8192])
 
 
+def emit_fec():
+    """Vectors for the "Conservative" error correction (decoder.py:304-323,738-780): 112-bit messages with no
+    error, 1-bit, 2-contiguous-bit, 2 scattered bits, wrong DF, 3 random flips -- and what the unmodified
+    decoder makes of them (parity verdict, bits after correction)."""
+    dec = rr.new_decoder(error_corr="Conservative")
+    rng = np.random.default_rng(1090)
+    base = np.concatenate((np.array([synth.hex_to_bits(h) for h in PUBLIC_DF17]), synth.df17_messages(rng, 594)))
+    msgs, kinds = [], []
+    for k, m in enumerate(base):
+        b = m.copy()
+        kind = k % 6
+        if kind == 1:
+            b[rng.integers(0, 112)] ^= 1
+        elif kind == 2:
+            i = rng.integers(0, 111)
+            b[i] ^= 1
+            b[i + 1] ^= 1
+        elif kind == 3:
+            b[rng.integers(0, 112)] ^= 1
+            b[rng.integers(0, 112)] ^= 1
+        elif kind == 4:
+            b[:5] = (0, 1, 0, 1, 1)
+        elif kind == 5:
+            b[rng.integers(5, 112, 3)] ^= 1
+        msgs.append(b)
+        kinds.append(kind)
+    msgs = np.array(msgs, np.uint8)
+    out = [rr.conservative_fix(b, dec) for b in msgs]
+    passed = np.array([o[0] for o in out], np.uint8)
+    after = np.array([o[1] for o in out], np.uint8)
+    np.savez_compressed(os.path.join(OUT, "fec_vectors.npz"), bits_in=np.packbits(msgs, axis=1),
+                        kind=np.array(kinds, np.uint8), passed=passed, bits_out=np.packbits(after, axis=1))
+    print("fec_vectors: %d messages, %d pass after correction, %d changed" % (
+        len(msgs), int(passed.sum()), int(np.any(after != msgs, axis=1).sum())))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fec":
+        emit_fec()
+    else:
+        main()
+        emit_fec()

@@ -9,7 +9,8 @@ SNR_TOL_DB = 1e-4     # BASELINE.json north_star: "reported SNR matches within 1
 
 
 def case_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in names if n != "fec_vectors")
 
 
 class Chunking(object):
@@ -64,3 +65,11 @@ def snr_close(a, b, tol=SNR_TOL_DB):
     if inf.any() and not np.array_equal(a[inf], b[inf]):
         return False
     return bool(np.all(np.abs(a[fin] - b[fin]) <= tol))
+
+
+def fec_vectors():
+    """(bits_in uint8[n,112], passed uint8[n], bits_out uint8[n,112]) from the reference decoder run with
+    error_corr="Conservative" (golden/make_golden.py:emit_fec)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "fec_vectors.npz"))
+    unpack = lambda a: np.unpackbits(a, axis=1)[:, :112]
+    return unpack(z["bits_in"]), z["passed"], unpack(z["bits_out"])

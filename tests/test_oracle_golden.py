@@ -63,3 +63,13 @@ def test_public_df17_crc():
     assert ao.crc_pass(bad) == 0 and co.crc_pass(bad) == 0
     df11 = synth.hex_to_bits("5D4840D6" + "0" * 20)
     assert ao.crc_pass(df11) == 0 and co.crc_pass(df11) == 0      # not DF17-19 -> filtered (decoder.py:667)
+
+
+def test_conservative_fec_matches_reference_decoder():
+    bits_in, passed, bits_out = G.fec_vectors()
+    assert len(bits_in) == 600 and 0 < passed.sum() < 600
+    for b, p, o in zip(bits_in, passed, bits_out):
+        p2, fixed, o2 = ao.conservative_fix(b)
+        assert p2 == p and np.array_equal(o2, o)
+        assert fixed == int(p and not ao.crc_pass(b))
+    assert len(ao.fec_table(112)) == 223          # 112 one-bit + 111 two-bit patterns (decoder.py:271-273)
