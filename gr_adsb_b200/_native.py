@@ -67,6 +67,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if "ADSB_B200_LIB" not in os.environ:
+        try:
+            build()           # no-op when the in-tree library is newer than its sources
+        except Exception as e:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError("%s is not built and nvcc failed (%s): run "
+                                   "`python -c 'import __graft_entry__ as g; g.build()'`" % (LIB_PATH, e))
     if not os.path.isfile(LIB_PATH):
         raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
