@@ -17,7 +17,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kLeftHalo = 128;      // samples staged left of a tile: 100 (noise window) + run look-back
 constexpr int kNoise = 100;         // framer.py:31 NUM_NOISE_SAMPLES
 constexpr int kMsgBits = 112;       // demod.py:29
-constexpr int kStage = 64;          // candidate records staged in shared memory per batch
 constexpr unsigned kFull = 0xffffffffu;
 
 // flags in Header.flags

@@ -56,7 +56,6 @@ struct TileSmem {
     unsigned short *xmask;  // T/16   extra candidate bits (by fall position) from the long-run pass
     unsigned short *xlong;  // T/16   which of them are long-run entries
     unsigned short *slow;   // kSlowCap fall slots
-    Rec *stage;             // kStage
     int *scratch;           // 64 ints: slots below + per-warp reduction cells
 };
 
@@ -70,7 +69,6 @@ __host__ __device__ inline size_t tile_smem_bytes(int T, int rh)
     b += align16(((size_t)T / 2 + 2) * 2);
     b += align16((size_t)(T / 16) * 2) * 2;
     b += align16((size_t)kSlowCap * 2);
-    b += (size_t)kStage * sizeof(Rec);
     b += 64 * 4;
     return b;
 }
@@ -91,8 +89,6 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
     raw += align16((size_t)(T / 16) * 2);
     s.slow = reinterpret_cast<unsigned short *>(raw);
     raw += align16((size_t)kSlowCap * 2);
-    s.stage = reinterpret_cast<Rec *>(raw);
-    raw += (size_t)kStage * sizeof(Rec);
     s.scratch = reinterpret_cast<int *>(raw);
     return s;
 }
@@ -749,8 +745,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     }
 }
 
-// ---- phase 3 of one tile, by a group of n_warps warps (gtid = thread index inside the group; needs
-// n_warps * 32 >= 2 * kStage for the copy-out) ------------------------------------------------------------------
+// ---- phase 3 of one tile, by a group of n_warps warps (tid = thread index inside the group) -------------------
 template <int SPS, bool C64, class GB>
 __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const int tid,
                                            const int n_warps, const GB gb)
@@ -772,52 +767,46 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     // PPM slice/CRC -- spread over the eight warps; edges / long runs: one warp per candidate, both roles
     const Access<C64> X{P, sm.mag, w0, S};
     const int sps_rt = SPS ? SPS : P.sps;
-    for (int b0 = 0; b0 < n_cand; b0 += kStage) {
-        const int nb = min(kStage, n_cand - b0);
-        const int n_tasks = ((nb + 1) >> 1) * 2;
-        for (int t = wid; t < n_tasks; t += n_warps) {
-            const int c = (t >> 1) * 2;
-            const bool two = c + 1 < nb;
-            const unsigned e0 = sm.list[b0 + c];
-            const unsigned e1 = two ? sm.list[b0 + c + 1] : e0;
-            if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
-                const int kp = (lane & 16) ? (int)e1 : (int)e0;
-                const int cc = c + ((lane >> 4) & (two ? 1 : 0));
-                const bool wr = two || !(lane & 16);
-                if (t & 1)
-                    slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, sm.stage[cc]);
-                else
-                    slice_pair_snr<SPS ? SPS : 2, C64>(P, sm.mag + kp, w0 + kp, lane, wr, sm.stage[cc]);
-                continue;
-            }
-            if (t & 1) continue;                            // generic path: the even task does both roles
-            unsigned crc_t[4];
+    // records go straight to this tile's block of the candidate array (the two tasks of a pair fill
+    // disjoint fields), so no staging buffer and no barrier after the slicing
+    const int n_tasks = ((n_cand + 1) >> 1) * 2;
+    for (int t = wid; t < n_tasks; t += n_warps) {
+        const int c = (t >> 1) * 2;
+        const bool two = c + 1 < n_cand;
+        const unsigned e0 = sm.list[c];
+        const unsigned e1 = two ? sm.list[c + 1] : e0;
+        if (g_off + (unsigned)c + 1u >= P.cand_cap) {
+            if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
+            continue;
+        }
+        if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
+            const int kp = (lane & 16) ? (int)e1 : (int)e0;
+            const int cc = c + ((lane >> 4) & (two ? 1 : 0));
+            const bool wr = two || !(lane & 16);
+            Rec &rec = P.cand[g_off + cc];
+            if (t & 1)
+                slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, rec);
+            else
+                slice_pair_snr<SPS ? SPS : 2, C64>(P, sm.mag + kp, w0 + kp, lane, wr, rec);
+            continue;
+        }
+        if (t & 1) continue;                            // generic path: the even task does both roles
+        unsigned crc_t[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
-            for (int q = 0; q < (two ? 2 : 1); q++) {
-                const unsigned e = q ? e1 : e0;
-                const int kf = e & 0x7fff;
-                Rec &rec = sm.stage[c + q];
-                if (e >> 15) {
-                    long long p;
-                    resolve_long<C64>(P, sm, w0, kf, lane, p);
-                    slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
-                } else {
-                    const float *mp = sm.mag + kf;              // list holds the centre slot
-                    slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
-                }
+        for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
+        for (int q = 0; q < (two ? 2 : 1); q++) {
+            const unsigned e = q ? e1 : e0;
+            const int kf = e & 0x7fff;
+            Rec &rec = P.cand[g_off + c + q];
+            if (e >> 15) {
+                long long p;
+                resolve_long<C64>(P, sm, w0, kf, lane, p);
+                slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
+            } else {
+                const float *mp = sm.mag + kf;              // list holds the centre slot
+                slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
             }
         }
-        gb.sync();
-        // coalesced copy-out: 2 x 16 bytes per record
-        if (tid < nb * 2) {
-            const unsigned slot = g_off + b0 + (tid >> 1);
-            if (slot < P.cand_cap)
-                reinterpret_cast<uint4 *>(P.cand + slot)[tid & 1] = reinterpret_cast<const uint4 *>(sm.stage + (tid >> 1))[tid & 1];
-            else if ((tid & 1) == 0)
-                atomicOr(&P.hdr->flags, kFlagCandOverflow);
-        }
-        if (b0 + kStage < n_cand) gb.sync();            // the staging area is reused by the next batch
     }
 }
 
