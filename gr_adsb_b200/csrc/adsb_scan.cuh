@@ -579,6 +579,25 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         lmask[ci] = lm;
     }
 
+    // ---- per-warp candidate counts, edge flags, last pulse -> shared memory; the barrier that publishes them
+    // also tells whether any run was deferred (rare), in which case the counts are redone after that pass ----
+    int (*s_cnt)[kWarps] = reinterpret_cast<int (*)[kWarps]>(sm.scratch + kScrCnt);
+    int *s_max = sm.scratch + kScrMax;
+    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + kScrFlag);
+    int wtot[NCH];
+#pragma unroll
+    for (int ci = 0; ci < NCH; ci++) wtot[ci] = __reduce_add_sync(kFull, __popc(cmask[ci]));
+    {
+        const unsigned f = __reduce_or_sync(kFull, tflags);
+        const int m = __reduce_max_sync(kFull, tmax);
+        if (lane == 0) {
+#pragma unroll
+            for (int ci = 0; ci < NCH; ci++) s_cnt[ci][wid] = wtot[ci];
+            s_flag[wid] = f;
+            s_max[wid] = m;
+        }
+    }
+
     // ---- long runs (rare): one warp per deferred fall ----
     long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + kScrMaxLong);
     if (gb.sync_or(have_long)) {
@@ -647,28 +666,17 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 lmask[ci] |= sm.xlong[c];
             }
         }
+#pragma unroll
+        for (int ci = 0; ci < NCH; ci++) {
+            wtot[ci] = __reduce_add_sync(kFull, __popc(cmask[ci]));
+            if (lane == 0) s_cnt[ci][wid] = wtot[ci];
+        }
+        gb.sync();
     } else if (tid == 0) {
         s_max_long = -1;
     }
 
-    // ---- ordered compaction of this tile's candidates into sm.list; per-tile reductions ----
-    int (*s_cnt)[kWarps] = reinterpret_cast<int (*)[kWarps]>(sm.scratch + kScrCnt);
-    int *s_max = sm.scratch + kScrMax;
-    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + kScrFlag);
-    int wtot[NCH];
-#pragma unroll
-    for (int ci = 0; ci < NCH; ci++) wtot[ci] = __reduce_add_sync(kFull, __popc(cmask[ci]));
-    {
-        const unsigned f = __reduce_or_sync(kFull, tflags);
-        const int m = __reduce_max_sync(kFull, tmax);
-        if (lane == 0) {
-#pragma unroll
-            for (int ci = 0; ci < NCH; ci++) s_cnt[ci][wid] = wtot[ci];
-            s_flag[wid] = f;
-            s_max[wid] = m;
-        }
-    }
-    gb.sync();
+    // ---- ordered compaction of this tile's candidates into sm.list ----
     // candidates are rare: only warps that hold some compute their slots
     bool any_here = false;
 #pragma unroll
