@@ -20,6 +20,7 @@ HIT_CRC_OK = 0x2
 HIT_LATE_TAG = 0x4
 HIT_FEC_FIXED = 0x8
 FEC_NONE, FEC_CONSERVATIVE = 0, 1
+FMT_F32, FMT_C64, FMT_SC16 = 0, 1, 2
 CARRY_USED_ON_DEVICE = -(1 << 63)
 
 HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
@@ -205,14 +206,16 @@ class Context(object):
         return bits, valid
 
     def burst_work(self, buf, n_out=None, lead=None, threshold=0.01, base=0, cap=None):
-        """Fused path over a host buffer (float32 |IQ|^2 or complex64 IQ) -> structured hits array."""
+        """Fused path over a host buffer (float32 |IQ|^2, complex64 IQ or int16[n,2] sc16 IQ) -> structured hits."""
         buf = np.ascontiguousarray(buf)
         if buf.dtype == np.complex64:
-            c64 = 1
+            c64 = FMT_C64
         elif buf.dtype == np.float32:
-            c64 = 0
+            c64 = FMT_F32
+        elif buf.dtype == np.int16 and buf.ndim == 2 and buf.shape[1] == 2:
+            c64 = FMT_SC16                       # interleaved int16 I/Q, value = int * 2**-15
         else:
-            raise TypeError("burst_work takes float32 or complex64")
+            raise TypeError("burst_work takes float32 |IQ|^2, complex64 IQ or int16[n,2] IQ")
         n_in = len(buf)
         if lead is None:
             lead = self.hist if n_out is None else int(n_out) + self.hist - n_in

@@ -169,35 +169,45 @@ void crc_table(unsigned *t)
     }
 }
 
-template <int SPS, bool C64>
+template <int SPS, int FMT>
 cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s)
 {
     const size_t smem = tile_smem_bytes(Geo<SPS>::T, P.rh);
     static size_t configured = 0;   // per instantiation; one device per process in practice
     if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, C64>,
+        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(scan_slice_kernel<SPS, C64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    scan_slice_kernel<SPS, C64><<<n_blocks, kThreads, smem, s>>>(P);
+    scan_slice_kernel<SPS, FMT><<<n_blocks, kThreads, smem, s>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P0, bool c64, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
+template <int SPS>
+cudaError_t launch_scan_f(const ScanParams &P, int fmt, unsigned n_blocks, cudaStream_t s)
+{
+    switch (fmt) {
+    case kFmtC64: return launch_scan_t<SPS, kFmtC64>(P, n_blocks, s);
+    case kFmtSC16: return launch_scan_t<SPS, kFmtSC16>(P, n_blocks, s);
+    default: return launch_scan_t<SPS, kFmtF32>(P, n_blocks, s);
+    }
+}
+
+cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P0, int fmt, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
 {
     if (n_blocks == 0) return cudaSuccess;
     ScanParams P = P0;
     P.tile_first = tile_first;
     P.n_tiles_launch = n_blocks;
     switch (c->sps) {
-    case 2: return c64 ? launch_scan_t<2, true>(P, n_blocks, s) : launch_scan_t<2, false>(P, n_blocks, s);
-    case 4: return c64 ? launch_scan_t<4, true>(P, n_blocks, s) : launch_scan_t<4, false>(P, n_blocks, s);
-    case 8: return c64 ? launch_scan_t<8, true>(P, n_blocks, s) : launch_scan_t<8, false>(P, n_blocks, s);
-    default: return c64 ? launch_scan_t<0, true>(P, n_blocks, s) : launch_scan_t<0, false>(P, n_blocks, s);
+    case 2: return launch_scan_f<2>(P, fmt, n_blocks, s);
+    case 4: return launch_scan_f<4>(P, fmt, n_blocks, s);
+    case 8: return launch_scan_f<8>(P, fmt, n_blocks, s);
+    default: return launch_scan_f<0>(P, fmt, n_blocks, s);
     }
 }
 
@@ -577,7 +587,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
                         size_t halo_left, float threshold, int64_t base, int64_t eob_in, void *stream,
                         const adsb_hit **d_hits)
 {
-    if (!ctx || !d_in) return ADSB_E_INVAL;
+    if (!ctx || !d_in || is_c64 < 0 || is_c64 > 2) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, halo_left, true);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -588,7 +598,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
     if ((rc = begin_call(ctx, n_tiles, (long long)n_out, s))) return rc;
     ScanParams P = make_params(ctx, d_in, n_in, lead, n_out, halo_left, threshold, base, prev_bit, 1);
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], s));
-    CK(launch_scan(ctx, P, is_c64 != 0, 0u, (unsigned)n_tiles, s));
+    CK(launch_scan(ctx, P, is_c64, 0u, (unsigned)n_tiles, s));
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], s));
     if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], s));
@@ -695,11 +705,11 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
 int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size_t lead, size_t n_out,
                     float threshold, int64_t base, adsb_hit *hits, size_t cap, size_t *n_hits)
 {
-    if (!ctx || !in) return ADSB_E_INVAL;
+    if (!ctx || !in || is_c64 < 0 || is_c64 > 2) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, 0);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    const size_t isz = is_c64 ? 8 : 4;
+    const size_t isz = (is_c64 == kFmtC64) ? 8 : 4;
     if ((rc = ensure_input(ctx, n_in * isz))) return rc;
     const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
     if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
@@ -726,7 +736,7 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
             CK(cudaEventRecord(ctx->ev[ring], ctx->copy_stream));
             CK(cudaStreamWaitEvent(s, ctx->ev[ring], 0));
             ring = (ring + 1) % kEvRing;
-            if (ready > tiles_done) CK(launch_scan(ctx, P, is_c64 != 0, (unsigned)tiles_done, (unsigned)(ready - tiles_done), s));
+            if (ready > tiles_done) CK(launch_scan(ctx, P, is_c64, (unsigned)tiles_done, (unsigned)(ready - tiles_done), s));
             tiles_done = ready;
         }
     }
@@ -757,7 +767,7 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
     CK(cudaMemcpyAsync(ctx->d_in, in0, n_in * 4, cudaMemcpyHostToDevice, s));
     if ((rc = begin_call(ctx, n_tiles, (long long)n_out, s))) return rc;
     ScanParams P = make_params(ctx, ctx->d_in, n_in, 0, n_out, 0, threshold, 0, prev_bit, 0);
-    CK(launch_scan(ctx, P, false, 0u, (unsigned)n_tiles, s));
+    CK(launch_scan(ctx, P, kFmtF32, 0u, (unsigned)n_tiles, s));
     if ((rc = launch_resolve(ctx, n_tiles, 0, eob_in, s))) return rc;
     ctx->last.pending = true;
     ctx->last.n_out = (long long)n_out;

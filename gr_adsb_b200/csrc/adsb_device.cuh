@@ -56,7 +56,7 @@ struct Header {
 };
 
 struct ScanParams {
-    const void *in;        // float (|IQ|^2) or float2 (IQ)
+    const void *in;        // float (|IQ|^2), float2 (IQ) or short2 (sc16 IQ)
     long long n_arr;       // items in `in`
     long long lead;        // virtual zero items before in[0]; window index = array index + lead
     long long n_loc;       // lead + n_arr
@@ -122,22 +122,42 @@ __device__ __forceinline__ float mag2(float2 v)
     return __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
 }
 
-template <bool C64>
+// input sample formats of the scan kernel
+enum { kFmtF32 = 0,     // float32 |IQ|^2 (what framer.work() is handed)
+       kFmtC64 = 1,     // complex64 IQ (the USRP source's fc32 stream)
+       kFmtSC16 = 2 };  // interleaved int16 IQ, value = int * 2^-15 (the wire format of most SDRs)
+
+// |IQ|^2 of one sc16 sample (re in the low half): widen, scale by 2^-15 (exact), then as mag2()
+__device__ __forceinline__ float mag2_sc16(unsigned v)
+{
+    const float re = __fmul_rn(__int2float_rn((int)(short)(v & 0xffffu)), 3.0517578125e-05f);
+    const float im = __fmul_rn(__int2float_rn((int)(short)(v >> 16)), 3.0517578125e-05f);
+    return __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+}
+
+__device__ __forceinline__ unsigned ldg_stream_b32(const void *p)
+{
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <int FMT>
 __device__ __forceinline__ float load_x(const void *in, long long j)
 {
-    if (C64)
-        return mag2(ldg_stream_f2(reinterpret_cast<const float2 *>(in) + j));
+    if (FMT == kFmtC64) return mag2(ldg_stream_f2(reinterpret_cast<const float2 *>(in) + j));
+    if (FMT == kFmtSC16) return mag2_sc16(ldg_stream_b32(reinterpret_cast<const unsigned *>(in) + j));
     return ldg_stream_f1(reinterpret_cast<const float *>(in) + j);
 }
 
 // window sample i (any i): zeros outside the array / inside the virtual lead
-template <bool C64>
+template <int FMT>
 __device__ __forceinline__ float window_x(const ScanParams &P, long long i)
 {
     long long j = i - P.lead;
     if (j < 0 || j >= P.n_arr)
         return 0.0f;
-    return load_x<C64>(P.in, j);
+    return load_x<FMT>(P.in, j);
 }
 
 // total order on non-NaN floats as unsigned keys

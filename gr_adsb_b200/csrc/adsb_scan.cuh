@@ -154,7 +154,7 @@ __device__ __forceinline__ bool demod_in_range(const ScanParams &P, long long p)
 }
 
 // window sample i through shared memory when staged, global memory otherwise
-template <bool C64>
+template <int FMT>
 struct Access {
     const ScanParams &P;
     const float *mag;
@@ -164,7 +164,7 @@ struct Access {
     {
         const long long s = i - w0;
         if (s >= 0 && s < S) return mag[s];
-        return window_x<C64>(P, i);
+        return window_x<FMT>(P, i);
     }
 };
 
@@ -186,7 +186,7 @@ __device__ __forceinline__ int walk_back_smem(const unsigned *bits, int kf)
 // ---- long runs: warp-cooperative walk back to the rising edge ------------------------------------------
 // Fall at shared-memory slot kf (window index w0 + kf).  Returns false when the pulse has no rising edge
 // inside this window (framer.py:98-100).  All 32 lanes participate and get the same answer.
-template <bool C64>
+template <int FMT>
 __device__ bool resolve_long(const ScanParams &P, const TileSmem &sm, long long w0, int kf, int lane, long long &p)
 {
     // 1) bitmap in shared memory, 32 words per step
@@ -215,7 +215,7 @@ __device__ bool resolve_long(const ScanParams &P, const TileSmem &sm, long long 
         while (true) {
             const long long i = i0 - lane;
             bool below;
-            if (i >= 0) below = !(window_x<C64>(P, i) >= P.thr);
+            if (i >= 0) below = !(window_x<FMT>(P, i) >= P.thr);
             else if (i == -1) below = !(P.left_is_start && P.prev_bit);
             else below = true;
             const unsigned b = __ballot_sync(kFull, below);
@@ -241,8 +241,8 @@ __device__ bool resolve_long(const ScanParams &P, const TileSmem &sm, long long 
 }
 
 // 16-tap test by one warp through the generic accessor
-template <bool C64>
-__device__ __forceinline__ bool warp_match(const Access<C64> &X, long long p, int h, int lane)
+template <int FMT>
+__device__ __forceinline__ bool warp_match(const Access<FMT> &X, long long p, int h, int lane)
 {
     const float xp = X(p);
     const float half = __fmul_rn(xp, 0.5f);
@@ -297,7 +297,7 @@ __device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, lo
 // fully staged, so no edge cases.  mp = shared-memory address of the candidate's centre sample.  The work
 // of a pair is split into two independent roles taken by different warps: the noise median / SNR ratio,
 // and the PPM slice + CRC; they fill disjoint fields of the staged record.
-template <int SPS, bool C64>
+template <int SPS, int FMT>
 __device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float *mp, long long p, int lane,
                                                bool write, Rec &rec)
 {
@@ -308,8 +308,8 @@ __device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float 
     for (int r = 0; r < 8; r++) {
         const int e = r * 16 + hl;
         const float v = (e < kNoise) ? mp[e - kNoise] : 0.0f;
-        if (C64) {
-            // |IQ|^2 is never negative: the raw bits order like the values; NaN bits sort above +inf
+        if (FMT != kFmtF32) {
+            // |IQ|^2 computed here is never negative: the raw bits order like the values; NaN bits sort above +inf
             k[r] = (e < kNoise) ? __float_as_uint(v) : 0x7f800000u;
         } else {
             nan |= (e < kNoise) && (v != v);
@@ -320,7 +320,7 @@ __device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float 
     const int src = (lane & 16) | 6;                       // ranks 49, 50 -> position 8*6 + 1, 8*6 + 2
     const unsigned ka = __shfl_sync(kFull, k[1], src), kb = __shfl_sync(kFull, k[2], src);
     float med;
-    if (C64) {
+    if (FMT != kFmtF32) {
         const unsigned top = __shfl_sync(kFull, k[7], (lane & 16) | 15);
         med = __fmul_rn(__fadd_rn(__uint_as_float(ka), __uint_as_float(kb)), 0.5f);   // fl32(fl32(a+b)/2)
         if (top > 0x7f800000u) med = __int_as_float(0x7fc00000);
@@ -368,7 +368,7 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
 
 // ---- phases 1 + 2 of one tile, by the 256 scan threads (threads 0..255 of the CTA) --------------------------
 // On return (after the caller's next group barrier) sm.list, scratch[kScrNCand|kScrOff|kScrFast] are valid.
-template <int SPS, bool C64, class GB>
+template <int SPS, int FMT, class GB>
 __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const GB gb)
 {
     using G = Geo<SPS>;
@@ -391,15 +391,15 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         // gets to it, its loads are L2 hits instead of HBM round trips
         const long long ta = tile + P.prefetch_tiles;
         if (((unsigned)ta - P.fast_lo) <= P.fast_span) {
-            const char *base = reinterpret_cast<const char *>(P.in) + (ta * T - kLeftHalo) * (C64 ? 8 : 4);
-            constexpr int kLines = (kLeftHalo + T + G::RH) * (C64 ? 8 : 4) / 128;
+            const char *base = reinterpret_cast<const char *>(P.in) + (ta * T - kLeftHalo) * (FMT == kFmtC64 ? 8 : 4);
+            constexpr int kLines = (kLeftHalo + T + G::RH) * (FMT == kFmtC64 ? 8 : 4) / 128;
             for (int l = tid; l < kLines; l += kThreads)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
         }
     }
     if (fast) {
         constexpr int U = 6;
-        if (C64) {
+        if (FMT == kFmtC64) {
             const float2 *src = reinterpret_cast<const float2 *>(P.in) + (a0 - kLeftHalo) + tid;
 #pragma unroll
             for (int u0 = 0; u0 < G::NPT; u0 += U) {
@@ -411,6 +411,24 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 for (int u = 0; u < U; u++) {
                     if (u0 + u < G::NPT) {
                         const float x = mag2_packed(v[u]);
+                        sm.mag[(u0 + u) * kThreads + tid] = x;
+                        const unsigned w = __ballot_sync(kFull, x >= thr);
+                        if (lane == 0) sm.bits[(u0 + u) * kWarps + wid] = w;
+                    }
+                }
+            }
+        } else if (FMT == kFmtSC16) {
+            const unsigned *src = reinterpret_cast<const unsigned *>(P.in) + (a0 - kLeftHalo) + tid;
+#pragma unroll
+            for (int u0 = 0; u0 < G::NPT; u0 += U) {
+                unsigned v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_b32(src + (u0 + u) * kThreads);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (u0 + u < G::NPT) {
+                        const float x = mag2_sc16(v[u]);
                         sm.mag[(u0 + u) * kThreads + tid] = x;
                         const unsigned w = __ballot_sync(kFull, x >= thr);
                         if (lane == 0) sm.bits[(u0 + u) * kWarps + wid] = w;
@@ -438,7 +456,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     } else {
         for (int k = wid * 32; k < S; k += kThreads) {
             const long long i = w0 + k + lane;
-            const float v = (i >= 0 && i < P.n_loc) ? window_x<C64>(P, i) : 0.0f;
+            const float v = (i >= 0 && i < P.n_loc) ? window_x<FMT>(P, i) : 0.0f;
             bool bit = v >= thr;
             if (i < 0) bit = P.left_is_start ? (i == -1 && P.prev_bit) : false;
             sm.mag[k + lane] = v;
@@ -608,13 +626,13 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         if (tid == 0) s_max_long = -1;
         gb.sync();
         const int n_slow = sm.scratch[kScrSlowN];
-        const Access<C64> X{P, sm.mag, w0, S};
+        const Access<FMT> X{P, sm.mag, w0, S};
         if (n_slow <= kSlowCap) {
             for (int e = wid; e < n_slow; e += kWarps) {
                 const int kf = sm.slow[e];
                 long long p;
-                if (!resolve_long<C64>(P, sm, w0, kf, lane, p)) continue;
-                const bool m = warp_match<C64>(X, p, h, lane);
+                if (!resolve_long<FMT>(P, sm, w0, kf, lane, p)) continue;
+                const bool m = warp_match<FMT>(X, p, h, lane);
                 if (lane == 0) {
                     atomicMax(&s_max_long, p);
                     if (m) {
@@ -645,8 +663,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     const int run = __clz(~(W << (32 - pos)));
                     if (fast ? (run <= G::LMAX) : (run < pos)) continue;     // handled as a short run already
                     long long p;
-                    if (!resolve_long<C64>(P, sm, w0, k0 + b, lane, p)) continue;
-                    const bool m = warp_match<C64>(X, p, h, lane);
+                    if (!resolve_long<FMT>(P, sm, w0, k0 + b, lane, p)) continue;
+                    const bool m = warp_match<FMT>(X, p, h, lane);
                     if (lane == 0) {
                         atomicMax(&s_max_long, p);
                         if (m) {
@@ -754,7 +772,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 }
 
 // ---- phase 3 of one tile, by a group of n_warps warps (tid = thread index inside the group) -------------------
-template <int SPS, bool C64, class GB>
+template <int SPS, int FMT, class GB>
 __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const int tid,
                                            const int n_warps, const GB gb)
 {
@@ -773,7 +791,7 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
     // interior tiles: candidates go in pairs (half-warp each) and every pair is two tasks -- median/SNR and
     // PPM slice/CRC -- spread over the eight warps; edges / long runs: one warp per candidate, both roles
-    const Access<C64> X{P, sm.mag, w0, S};
+    const Access<FMT> X{P, sm.mag, w0, S};
     const int sps_rt = SPS ? SPS : P.sps;
     // records go straight to this tile's block of the candidate array (the two tasks of a pair fill
     // disjoint fields), so no staging buffer and no barrier after the slicing
@@ -795,7 +813,7 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
             if (t & 1)
                 slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, rec);
             else
-                slice_pair_snr<SPS ? SPS : 2, C64>(P, sm.mag + kp, w0 + kp, lane, wr, rec);
+                slice_pair_snr<SPS ? SPS : 2, FMT>(P, sm.mag + kp, w0 + kp, lane, wr, rec);
             continue;
         }
         if (t & 1) continue;                            // generic path: the even task does both roles
@@ -808,7 +826,7 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
             Rec &rec = P.cand[g_off + c + q];
             if (e >> 15) {
                 long long p;
-                resolve_long<C64>(P, sm, w0, kf, lane, p);
+                resolve_long<FMT>(P, sm, w0, kf, lane, p);
                 slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
             } else {
                 const float *mp = sm.mag + kf;              // list holds the centre slot
@@ -819,16 +837,16 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
 }
 
 // ---- the kernel: one CTA (8 warps) per tile, phases in sequence ---------------------------------------------
-template <int SPS, bool C64>
+template <int SPS, int FMT>
 __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) scan_slice_kernel(const ScanParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileSmem sm = carve(smem_raw, Geo<SPS>::T, SPS ? Geo<SPS>::RH : P.rh);
     const long long tile = (long long)P.tile_first + blockIdx.x;
     const CtaBar gb;
-    scan_tile<SPS, C64>(P, sm, tile, gb);
+    scan_tile<SPS, FMT>(P, sm, tile, gb);
     gb.sync();
-    slice_tile<SPS, C64>(P, sm, tile, (int)threadIdx.x, kWarps, gb);
+    slice_tile<SPS, FMT>(P, sm, tile, (int)threadIdx.x, kWarps, gb);
 }
 
 }  // namespace adsb

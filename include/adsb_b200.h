@@ -32,6 +32,10 @@ extern "C" {
 
 #define ADSB_B200_ABI_VERSION 1
 
+#define ADSB_FMT_F32 0
+#define ADSB_FMT_C64 1
+#define ADSB_FMT_SC16 2
+
 enum {
     ADSB_OK = 0,
     ADSB_E_INVAL = -1,     /* bad argument (odd sps, null pointer, sizes that do not fit max_items ...) */
@@ -115,9 +119,10 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
 int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *sob_idx, size_t n_tags,
                     uint8_t *bits, uint8_t *valid);
 
-/* Fused path over a HOST buffer: optional |IQ|^2 (is_c64: in = interleaved re,im float32 pairs,
- * n_in complex items; else float32 |IQ|^2), framer, demod and parity check in one pass on the
- * GPU.  The window is `lead` zero items followed by in[0:n_in]; n_out + 8*sps - 1 == lead + n_in.
+/* Fused path over a HOST buffer: |IQ|^2 where needed, framer, demod and parity check in one pass on the
+ * GPU.  `is_c64` selects the item format: ADSB_FMT_F32 (0) float32 |IQ|^2, ADSB_FMT_C64 (1) interleaved re,im
+ * float32 pairs, ADSB_FMT_SC16 (2) interleaved re,im int16 with value = int * 2^-15 (UHD sc16 wire format /
+ * blocks.interleaved_short_to_complex with scale 32768); n_in counts items (complex samples).  The window is `lead` zero items followed by in[0:n_in]; n_out + 8*sps - 1 == lead + n_in.
  * lead = 8*sps-1 with a freshly reset context reproduces a flowgraph's first work() call over
  * the whole buffer ("whole-buffer mode"); lead = 0 continues a stream whose history the caller
  * prepends, exactly like adsb_framer_work.  hits[i].idx = base + window index. */

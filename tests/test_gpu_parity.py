@@ -301,3 +301,19 @@ def test_conservative_error_correction_matches_reference_decoder():
     assert np.array_equal(g.unpack_bits(hits0), bits_in)
     assert not np.any(hits0["flags"] & g.HIT_FEC_FIXED)
     ctx.close()
+
+
+@pytest.mark.parametrize("sps,seed", [(2, 31), (8, 32), (6, 33)])
+def test_sc16_input_matches_oracle(sps, seed):
+    """interleaved int16 IQ widened on the device (value = int * 2^-15) must give exactly what
+    the complex64 path gives on the widened samples."""
+    n = (1 << 20) * (2 if sps >= 6 else 1)
+    d = synth.synth_numpy(n, sps=sps, n_bursts=int(n * 2e-3 * 2 / sps), seed=seed, noise_var=1e-3, amp_db=(-20.0, 0.0))
+    q = np.clip(np.round(d["iq"].view(np.float32).reshape(-1, 2) * 32768.0), -32768, 32767).astype(np.int16)
+    iq = (q.astype(np.float32) * np.float32(2.0 ** -15)).view(np.complex64).reshape(-1)
+    ref = co.run_stream(co.mag2(iq), sps * 1e6, 0.01, None)
+    ctx = ctx_for(sps, n)
+    hits = ctx.burst_work(q, threshold=0.01)
+    crc = np.array([co.crc_pass(b) for b in ref["pdu_bits"]], np.uint8)
+    check_fused(hits, sps, ref["tag_off"], ref["tag_snr"], ref["pdu_off"], ref["pdu_bits"], crc)
+    assert len(hits) > 20
