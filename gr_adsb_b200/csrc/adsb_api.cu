@@ -510,6 +510,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ALLOC(ctx->d_valid, ctx->tag_cap);
 #undef ALLOC
     if ((e = cudaMallocHost((void **)&ctx->h_stage, sizeof(HostStage))) != cudaSuccess) return die(ADSB_E_NOMEM, "pinned stage", e);
+    // the header's sticky carry_unstable counter survives init_header_kernel: start it from zero
+    if ((e = cudaMemset(ctx->d_hdr, 0, sizeof(Header))) != cudaSuccess) return die(ADSB_E_CUDA, "memset(header)", e);
     unsigned tab[kMsgBits];
     crc_table(tab);
     if ((e = cudaMemcpy(ctx->d_crc, tab, sizeof(tab), cudaMemcpyHostToDevice)) != cudaSuccess) return die(ADSB_E_CUDA, "crc table", e);
