@@ -98,6 +98,13 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
+_REF_SAMPLE = None      # bounded sample of the reference arm; inherited by the forked workers (no pickling)
+
+
+def _ref_worker(_):
+    return _cpu_worker((_REF_SAMPLE, None))
+
+
 def _cpu_worker(args):
     iq, chunk = args
     from oracle import adsb_oracle as ao
@@ -135,16 +142,16 @@ def run_reference_arm(args):
     dt = _cpu_worker((cal, None))[0]
     rate = len(cal) / dt
     per_worker = int(max(1 << 14, min(1 << 21, rate * 100.0 / (args.steps + args.warmup))))
-    one = synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1)["iq"]
-    shards = [one] * cores          # every core chews an independent copy of the same bounded sample
+    global _REF_SAMPLE
+    _REF_SAMPLE = synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1)["iq"]
     log("reference arm: %d cores, %d samples per core per step" % (cores, per_worker))
-    with mp.get_context("fork").Pool(cores) as pool:
+    with mp.get_context("fork").Pool(cores) as pool:       # every core chews the same bounded sample
         for _ in range(args.warmup):
-            pool.map(_cpu_worker, [(s, None) for s in shards])
+            pool.map(_ref_worker, range(cores), chunksize=1)
         t0 = time.perf_counter()
         crc = 0
         for _ in range(args.steps):
-            out = pool.map(_cpu_worker, [(s, None) for s in shards])
+            out = pool.map(_ref_worker, range(cores), chunksize=1)
             crc += sum(o[3] for o in out)
         dt = time.perf_counter() - t0
     total = per_worker * cores * args.steps
