@@ -137,12 +137,17 @@ def run_reference_arm(args):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    # calibrate on a small sample, then size the per-step sample so K+W steps take ~100 s
-    cal = synth.synth_numpy(1 << 17, sps=SPS, n_bursts=int((1 << 17) * DENSITY), seed=SEED)["iq"]
-    dt = _cpu_worker((cal, None))[0]
-    rate = len(cal) / dt
-    per_worker = int(max(1 << 14, min(1 << 21, rate * 100.0 / (args.steps + args.warmup))))
+    # calibrate with all cores busy (they slow each other down a lot), then size the per-step sample so that
+    # the K + W steps take ~100 s in total
     global _REF_SAMPLE
+    n_cal = 1 << 16
+    _REF_SAMPLE = synth.synth_numpy(n_cal, sps=SPS, n_bursts=int(n_cal * DENSITY), seed=SEED)["iq"]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_ref_worker, range(cores), chunksize=1)
+        t0 = time.perf_counter()
+        pool.map(_ref_worker, range(cores), chunksize=1)
+        per_core_rate = n_cal / (time.perf_counter() - t0)
+    per_worker = int(max(1 << 13, min(1 << 21, per_core_rate * 100.0 / (args.steps + args.warmup))))
     _REF_SAMPLE = synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1)["iq"]
     log("reference arm: %d cores, %d samples per core per step" % (cores, per_worker))
     with mp.get_context("fork").Pool(cores) as pool:       # every core chews the same bounded sample
