@@ -61,7 +61,8 @@ EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_creat
            "adsb_last_error", "adsb_reset_state", "adsb_get_state", "adsb_set_state", "adsb_get_counters",
            "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish",
            "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
-           "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev", "adsb_set_error_correction"]
+           "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev", "adsb_set_error_correction",
+           "adsb_burst_mag_out"]
 
 
 def lib():
@@ -105,6 +106,8 @@ def lib():
     L.adsb_demod_work.argtypes = [vp, vp, sz, vp, sz, vp, vp]
     L.adsb_burst_work.restype = i32
     L.adsb_burst_work.argtypes = [vp, vp, i32, sz, sz, sz, f32, i64, vp, sz, C.POINTER(sz)]
+    L.adsb_burst_mag_out.restype = i32
+    L.adsb_burst_mag_out.argtypes = [vp, vp, sz]
     L.adsb_burst_work_dev.restype = i32
     L.adsb_burst_work_dev.argtypes = [vp, vp, i32, sz, sz, sz, sz, f32, i64, i64, vp, C.POINTER(vp)]
     L.adsb_burst_finish.restype = i32
@@ -258,32 +261,34 @@ class Context(object):
         self._check(rc)
         return c.as_dict(), hits[:n.value]
 
+    def burst_mag_out(self, out):
+        """Fill the float32 array `out` with |IQ|^2 of the last len(out) items of the latest burst_work input
+        (computed on the device from the staged copy)."""
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        self._check(lib().adsb_burst_mag_out(self._h, _ptr(out), len(out)))
+        return out
 
-def _profile_methods():
-    def profile_enable(self, on=True):
-        self._check(lib().adsb_profile_enable(self._h, 1 if on else 0))
-
-    def profile_last(self):
-        a, b = C.c_float(), C.c_float()
-        self._check(lib().adsb_profile_last(self._h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+    # --- multi-GPU carry (gr_adsb_b200/sharding.py) -------------------------------------------------
     def burst_reresolve_dev(self, eob_in, stream=0):
         self._check(lib().adsb_burst_reresolve_dev(self._h, int(eob_in), C.c_void_p(stream)))
-    Context.burst_reresolve_dev = burst_reresolve_dev
 
     def burst_export_carry_dev(self, used_global, dev_ptr, stream=0):
         self._check(lib().adsb_burst_export_carry_dev(self._h, int(used_global), C.c_void_p(dev_ptr), C.c_void_p(stream)))
-    Context.burst_export_carry_dev = burst_export_carry_dev
 
     def burst_carry_round_dev(self, gathered_ptr, world, rank, final_check=False, stream=0):
         self._check(lib().adsb_burst_carry_round_dev(self._h, C.c_void_p(gathered_ptr), int(world), int(rank),
                                                       1 if final_check else 0, C.c_void_p(stream)))
-    Context.burst_carry_round_dev = burst_carry_round_dev
-    Context.profile_enable = profile_enable
-    Context.profile_last = profile_last
 
+    # --- measurement hook ------------------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._check(lib().adsb_profile_enable(self._h, 1 if on else 0))
 
-_profile_methods()
+    def profile_last(self):
+        """(scan_ms, resolve_ms) of the latest burst_work_dev, from CUDA events on its launch stream."""
+        a, b = C.c_float(), C.c_float()
+        self._check(lib().adsb_profile_last(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
 
 
 def unpack_bits(hits):

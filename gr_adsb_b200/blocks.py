@@ -183,10 +183,12 @@ class burst(gr.sync_block, _DeviceBlock):
                 if hits["flags"][k] & _native.HIT_DEMOD_VALID:
                     meta = pmt.to_pmt({"timestamp": self.start_timestamp + off / self.fs, "snr": snr})
                     self.message_port_pub(port, pmt.cons(meta, pmt.to_pmt(bits[k].copy())))
-        tail = in0[self.N_hist - 1:]
         if self.complex_input:
-            v = np.ascontiguousarray(tail).view(np.float32).reshape(-1, 2)
-            out0[:] = v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]
+            # the |IQ|^2 stream the removed complex_to_mag_squared block produced, from the device copy of in0
+            if out0.dtype == np.float32 and out0.flags["C_CONTIGUOUS"]:
+                ctx.burst_mag_out(out0)
+            else:
+                out0[:] = ctx.burst_mag_out(np.empty(N, np.float32))
         else:
-            out0[:] = tail
+            out0[:] = in0[self.N_hist - 1:]           # framer.py:181
         return N

@@ -45,6 +45,15 @@ __global__ void export_carry_kernel(const Header *h, long long base, long long u
     out[2] = used_from_dev ? h->carry_used : used_global;
 }
 
+// |IQ|^2 stream of a staged input (what blocks.complex_to_mag_squared handed downstream, adsb_rx.py:180)
+template <int FMT>
+__global__ void mag_out_kernel(const void *in, long long first, long long n, float *out)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = load_x<FMT>(in, first + i);
+}
+
 struct HostStage {
     Header hdr;
     Rec first[kFirstHits];
@@ -89,6 +98,15 @@ struct adsb_ctx {
     unsigned short *d_fec_fix;
     unsigned rerun_count;
     cudaEvent_t pev[3];
+    float *d_mag;                // |IQ|^2 output stream of adsb_burst_mag_out (allocated on first use)
+    size_t d_mag_cap;
+    int staged_fmt;              // format / item count of the input adsb_burst_work staged last (-1: none)
+    size_t staged_n;
+    bool scan_configured[3];     // per sample format: shared-memory attributes of the scan kernel set on this device
+    Rec *h_tmp;                  // host scratch of the two-block entry points
+    size_t h_tmp_cap;
+    unsigned char *h_bits;
+    size_t h_bits_cap;
     char err[256];
 };
 
@@ -104,6 +122,26 @@ int fail(adsb_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
     }
     return code;
 }
+
+// Entry points run on the context's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev;
+    cudaError_t status;
+    explicit DeviceGuard(int device) : prev(-1), status(cudaSuccess)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) status = cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define ON_DEVICE(ctx)                                                               \
+    DeviceGuard guard_((ctx)->device);                                               \
+    if (guard_.status != cudaSuccess) return fail((ctx), ADSB_E_CUDA, "cudaSetDevice", guard_.status)
 
 #define CK(call)                                                          \
     do {                                                                  \
@@ -169,45 +207,46 @@ void crc_table(unsigned *t)
     }
 }
 
+// `configured` = this context (one device, one sps) has already raised the kernel's shared-memory limits
 template <int SPS, int FMT>
-cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s)
+cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s, bool *configured)
 {
     const size_t smem = tile_smem_bytes(Geo<SPS>::T, P.rh);
-    static size_t configured = 0;   // per instantiation; one device per process in practice
-    if (configured < smem) {
+    if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        *configured = true;
     }
     scan_slice_kernel<SPS, FMT><<<n_blocks, kThreads, smem, s>>>(P);
     return cudaGetLastError();
 }
 
 template <int SPS>
-cudaError_t launch_scan_f(const ScanParams &P, int fmt, unsigned n_blocks, cudaStream_t s)
+cudaError_t launch_scan_f(const ScanParams &P, int fmt, unsigned n_blocks, cudaStream_t s, bool *configured)
 {
     switch (fmt) {
-    case kFmtC64: return launch_scan_t<SPS, kFmtC64>(P, n_blocks, s);
-    case kFmtSC16: return launch_scan_t<SPS, kFmtSC16>(P, n_blocks, s);
-    default: return launch_scan_t<SPS, kFmtF32>(P, n_blocks, s);
+    case kFmtC64: return launch_scan_t<SPS, kFmtC64>(P, n_blocks, s, configured);
+    case kFmtSC16: return launch_scan_t<SPS, kFmtSC16>(P, n_blocks, s, configured);
+    default: return launch_scan_t<SPS, kFmtF32>(P, n_blocks, s, configured);
     }
 }
 
-cudaError_t launch_scan(const adsb_ctx *c, const ScanParams &P0, int fmt, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
+cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
 {
     if (n_blocks == 0) return cudaSuccess;
     ScanParams P = P0;
     P.tile_first = tile_first;
     P.n_tiles_launch = n_blocks;
+    bool *configured = &c->scan_configured[fmt];
     switch (c->sps) {
-    case 2: return launch_scan_f<2>(P, fmt, n_blocks, s);
-    case 4: return launch_scan_f<4>(P, fmt, n_blocks, s);
-    case 8: return launch_scan_f<8>(P, fmt, n_blocks, s);
-    default: return launch_scan_f<0>(P, fmt, n_blocks, s);
+    case 2: return launch_scan_f<2>(P, fmt, n_blocks, s, configured);
+    case 4: return launch_scan_f<4>(P, fmt, n_blocks, s, configured);
+    case 8: return launch_scan_f<8>(P, fmt, n_blocks, s, configured);
+    default: return launch_scan_f<0>(P, fmt, n_blocks, s, configured);
     }
 }
 
@@ -408,7 +447,7 @@ const char *adsb_last_error(const adsb_ctx *ctx) { return ctx ? ctx->err : "null
 void adsb_destroy(adsb_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_in);
     cudaFree(ctx->d_cand);
@@ -425,7 +464,10 @@ void adsb_destroy(adsb_ctx *ctx)
     cudaFree(ctx->d_sob);
     cudaFree(ctx->d_bits);
     cudaFree(ctx->d_valid);
+    cudaFree(ctx->d_mag);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    free(ctx->h_tmp);
+    free(ctx->h_bits);
     for (int i = 0; i < kEvRing; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; i++)
@@ -444,7 +486,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ADSB_E_NODEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return ADSB_E_NODEVICE;
-    if (cudaSetDevice(device) != cudaSuccess) return ADSB_E_NODEVICE;
+    DeviceGuard guard(device);
+    if (guard.status != cudaSuccess) return ADSB_E_NODEVICE;
 
     adsb_ctx *ctx = new (std::nothrow) adsb_ctx();
     if (!ctx) return ADSB_E_NOMEM;
@@ -457,6 +500,7 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->max_items = max_items;
     ctx->prev_in0 = 0.0f;
     ctx->prev_eob = -1;
+    ctx->staged_fmt = -1;
     ctx->num_sms = prop.multiProcessorCount;
     {
         const char *e = getenv("ADSB_PREFETCH_TILES");      // tuning knob; default: two tiles per SM ahead
@@ -592,7 +636,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
     if (!ctx || !d_in || is_c64 < 0 || is_c64 > 2) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, halo_left, true);
     if (rc) return rc;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     const int prev_bit = (lead != 0) ? (0.0f >= threshold) : (ctx->prev_in0 >= threshold);
     const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
@@ -618,7 +662,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
 int adsb_burst_reresolve_dev(adsb_ctx *ctx, int64_t eob_in, void *stream)
 {
     if (!ctx || !ctx->last.pending) return ADSB_E_INVAL;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
     const long long n_tiles = tiles_for(ctx, ctx->last.n_out, ctx->last.lead);
     ctx->rerun_count++;
@@ -635,7 +679,7 @@ int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int wor
                                void *stream)
 {
     if (!ctx || !ctx->last.pending || !d_gathered || world < 1 || rank < 0 || rank >= world) return ADSB_E_INVAL;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
     carry_plan_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, reinterpret_cast<const long long *>(d_gathered), world, rank,
                                       63LL * ctx->sps, final_check);
@@ -650,7 +694,7 @@ int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int wor
 int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_out3, void *stream)
 {
     if (!ctx || !ctx->last.pending || !d_out3) return ADSB_E_INVAL;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
     export_carry_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, ctx->last.base, used_global, used_global == ADSB_CARRY_USED_ON_DEVICE,
                                         reinterpret_cast<long long *>(d_out3));
@@ -661,7 +705,7 @@ int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_o
 int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits)
 {
     if (!ctx || !ctx->last.pending) return ADSB_E_INVAL;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t s = ctx->last.stream;
     CK(cudaMemcpyAsync(&ctx->h_stage->hdr, ctx->d_hdr, sizeof(Header), cudaMemcpyDeviceToHost, s));
     if (hits && cap)
@@ -710,8 +754,9 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
     if (!ctx || !in || is_c64 < 0 || is_c64 > 2) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, 0);
     if (rc) return rc;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     const size_t isz = (is_c64 == kFmtC64) ? 8 : 4;
+    ctx->staged_fmt = -1;
     if ((rc = ensure_input(ctx, n_in * isz))) return rc;
     const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
     if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
@@ -743,6 +788,8 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
         }
     }
     if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
+    ctx->staged_fmt = is_c64;
+    ctx->staged_n = n_in;
     ctx->last.pending = true;
     ctx->last.n_out = (long long)n_out;
     ctx->last.lead = (long long)lead;
@@ -753,6 +800,37 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
     return adsb_burst_finish(ctx, nullptr, hits, cap, n_hits);
 }
 
+int adsb_burst_mag_out(adsb_ctx *ctx, float *out, size_t n_out)
+{
+    if (!ctx || !out) return ADSB_E_INVAL;
+    if (ctx->staged_fmt < 0 || n_out == 0 || n_out > ctx->staged_n)
+        return fail(ctx, ADSB_E_INVAL, "adsb_burst_mag_out: needs a preceding adsb_burst_work with n_in >= n_out");
+    ON_DEVICE(ctx);
+    if (ctx->d_mag_cap < n_out) {
+        cudaFree(ctx->d_mag);
+        ctx->d_mag = nullptr;
+        ctx->d_mag_cap = 0;
+        const size_t want = ctx->max_items > n_out ? ctx->max_items : n_out;
+        cudaError_t e = cudaMalloc((void **)&ctx->d_mag, want * sizeof(float));
+        if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, "cudaMalloc(|IQ|^2 output)", e);
+        ctx->d_mag_cap = want;
+    }
+    cudaStream_t s = ctx->stream;
+    const long long first = (long long)(ctx->staged_n - n_out);
+    size_t want_blocks = (n_out + kThreads * 4 - 1) / (kThreads * 4);
+    const size_t max_blocks = (size_t)ctx->num_sms * 8;
+    const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    switch (ctx->staged_fmt) {
+    case kFmtC64: mag_out_kernel<kFmtC64><<<blocks, kThreads, 0, s>>>(ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    case kFmtSC16: mag_out_kernel<kFmtSC16><<<blocks, kThreads, 0, s>>>(ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    default: mag_out_kernel<kFmtF32><<<blocks, kThreads, 0, s>>>(ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_mag, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ADSB_OK;
+}
+
 int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out, float threshold,
                      int64_t *hit_idx, float *hit_snr, size_t cap, size_t *n_hits)
 {
@@ -760,8 +838,9 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
     *n_hits = 0;
     int rc = check_geometry(ctx, n_in, 0, n_out, 0);
     if (rc) return rc;
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if ((rc = ensure_input(ctx, n_in * 4))) return rc;
+    ctx->staged_fmt = -1;
     cudaStream_t s = ctx->stream;
     const long long n_tiles = tiles_for(ctx, (long long)n_out, 0);
     const int prev_bit = ctx->prev_in0 >= threshold;
@@ -779,9 +858,14 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
     ctx->last.left_is_start = 1;
     ctx->last.stream = s;
     // header + hits in one synchronisation (the first kFirstHits ride along with the header)
-    size_t tcap = n_out / (size_t)(63 * ctx->sps) + 2;
-    Rec *tmp = (Rec *)malloc(tcap * sizeof(Rec));
-    if (!tmp) return fail(ctx, ADSB_E_NOMEM, "malloc");
+    const size_t tcap = n_out / (size_t)(63 * ctx->sps) + 2;      // blanking bounds the hits of one call
+    if (ctx->h_tmp_cap < tcap) {
+        free(ctx->h_tmp);
+        ctx->h_tmp = (Rec *)malloc(tcap * sizeof(Rec));
+        ctx->h_tmp_cap = ctx->h_tmp ? tcap : 0;
+        if (!ctx->h_tmp) return fail(ctx, ADSB_E_NOMEM, "malloc(hit scratch)");
+    }
+    Rec *tmp = ctx->h_tmp;
     size_t n = 0;
     rc = adsb_burst_finish(ctx, nullptr, reinterpret_cast<adsb_hit *>(tmp), tcap, &n);
     if (rc == ADSB_OK) {
@@ -795,7 +879,6 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
             }
         }
     }
-    free(tmp);
     return rc;
 }
 
@@ -806,9 +889,10 @@ int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *so
     if (n_tags == 0) return ADSB_OK;             // the common work() call: nothing tagged, nothing to do
     if (!in0 || !sob_idx || !bits || !valid) return ADSB_E_INVAL;
     if (n > ctx->max_items + (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "n exceeds max_items");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     int rc;
     if ((rc = ensure_input(ctx, n * 4))) return rc;
+    ctx->staged_fmt = -1;
     if (n_tags > ctx->tag_cap) {
         cudaFree(ctx->d_sob);
         cudaFree(ctx->d_bits);
@@ -848,8 +932,15 @@ int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *so
     if (all) {
         CK(cudaMemcpy(bits, ctx->d_bits, n_tags * kMsgBits, cudaMemcpyDeviceToHost));
     } else {
+        if (ctx->h_bits_cap < n_tags * kMsgBits) {
+            free(ctx->h_bits);
+            ctx->h_bits = (unsigned char *)malloc(n_tags * kMsgBits);
+            ctx->h_bits_cap = ctx->h_bits ? n_tags * kMsgBits : 0;
+            if (!ctx->h_bits) return fail(ctx, ADSB_E_NOMEM, "malloc(bit scratch)");
+        }
+        CK(cudaMemcpy(ctx->h_bits, ctx->d_bits, n_tags * kMsgBits, cudaMemcpyDeviceToHost));
         for (size_t t = 0; t < n_tags; t++)
-            if (valid[t]) CK(cudaMemcpy(bits + t * kMsgBits, ctx->d_bits + t * kMsgBits, kMsgBits, cudaMemcpyDeviceToHost));
+            if (valid[t]) memcpy(bits + t * kMsgBits, ctx->h_bits + t * kMsgBits, kMsgBits);
     }
     return ADSB_OK;
 }

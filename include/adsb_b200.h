@@ -129,6 +129,12 @@ int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *so
 int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size_t lead, size_t n_out,
                     float threshold, int64_t base, adsb_hit *hits, size_t cap, size_t *n_hits);
 
+/* out[0:n_out] = |IQ|^2 of the LAST n_out items handed to the most recent adsb_burst_work, computed on the
+ * device from the copy still staged there (ADSB_FMT_F32 input: the items themselves).  This is the stream
+ * blocks.complex_to_mag_squared (examples/adsb_rx.py:180,195-197) fed to the framer and the time sink; the fused
+ * "burst" block with complex input writes it to its output port, as framer.py:181 does with its input. */
+int adsb_burst_mag_out(adsb_ctx *ctx, float *out, size_t n_out);
+
 /* Same, for a buffer already resident in device memory; runs asynchronously on CUDA stream
  * `stream` (a cudaStream_t, may be NULL = the context's own stream) and leaves the results on the
  * device (n_out + 8*sps - 1 <= lead + n_in here: items past that are a right halo): *d_hits is a device pointer to adsb_hit[] owned by the context (valid until the next

@@ -240,6 +240,9 @@ def _run_burst_block(blk, x, sizes, thresholds=None):
         blk._nitems_read = pos
         nt0, nm0 = len(blk._tags_out), len(blk._msgs["demodulated"])
         assert blk.work([in0], [out0]) == n
+        # output port: the |IQ|^2 stream (complex input) / the input itself (framer.py:181), bit for bit
+        want = ao.mag2(x[pos:pos + n]) if dt == np.complex64 else x[pos:pos + n]
+        assert np.array_equal(out0.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
         for t in blk._tags_out[nt0:]:
             assert t.key == "burst" and t.value[0] == "SOB" and t.srcid == "framer"
             tags.append((int(t.offset), t.value[1]))
