@@ -10,7 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.environ.get("ADSB_B200_LIB", os.path.join(CSRC, "libadsb_b200.so"))
+BUILT_LIB = os.path.join(CSRC, "libadsb_b200.so")                 # what build() produces
+LIB_PATH = os.environ.get("ADSB_B200_LIB", BUILT_LIB)
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "adsb_b200.h")
 
 ADSB_OK = 0
@@ -46,13 +47,13 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into csrc/libadsb_b200.so (in-tree, so it travels with the repo)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
     srcs.append(HEADER)
-    if not force and os.path.isfile(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
+    if not force and os.path.isfile(BUILT_LIB) and all(os.path.getmtime(BUILT_LIB) >= os.path.getmtime(s) for s in srcs):
+        return BUILT_LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(CSRC, "adsb_api.cu")]
+          ["-o", BUILT_LIB, os.path.join(CSRC, "adsb_api.cu")]
     subprocess.check_call(cmd)
-    return LIB_PATH
+    return BUILT_LIB
 
 
 _lib = None

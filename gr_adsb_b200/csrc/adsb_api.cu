@@ -221,7 +221,7 @@ cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s
         if (e != cudaSuccess) return e;
         *configured = true;
     }
-    scan_slice_kernel<SPS, FMT><<<n_blocks, kThreads, smem, s>>>(P);
+    ADSB_LAUNCH((scan_slice_kernel<SPS, FMT>), n_blocks, kThreads, smem, s, P);
     return cudaGetLastError();
 }
 
@@ -340,11 +340,11 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     const unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
     const unsigned cblocks = cap_blocks;
     if (rerun)
-        reset_resolve_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, R.dev_carry);
+        ADSB_LAUNCH(reset_resolve_kernel, 1, 1, 0, s, ctx->d_hdr, R.dev_carry);
     else
-        gather_kernel<<<gblocks, kThreads, 0, s>>>(R);
-    chain_kernel<<<cap_blocks, kThreads, 0, s>>>(R);
-    compact_kernel<<<cblocks, kThreads, 0, s>>>(R);
+        ADSB_LAUNCH(gather_kernel, gblocks, kThreads, 0, s, R);
+    ADSB_LAUNCH(chain_kernel, cap_blocks, kThreads, 0, s, R);
+    ADSB_LAUNCH(compact_kernel, cblocks, kThreads, 0, s, R);
     if (ctx->fec_mode == ADSB_FEC_CONSERVATIVE) {
         FecParams F;
         F.hits = ctx->d_hits;
@@ -353,7 +353,7 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
         F.t25 = ctx->d_fec_t25;
         F.keys = ctx->d_fec_keys;
         F.fix = ctx->d_fec_fix;
-        fec_kernel<<<cap_blocks, kThreads, 0, s>>>(F);
+        ADSB_LAUNCH(fec_kernel, cap_blocks, kThreads, 0, s, F);
     }
     CK(cudaGetLastError());
     return ADSB_OK;
@@ -370,7 +370,7 @@ int zero_cand_totals(adsb_ctx *ctx, long long n_out, cudaStream_t s)
 
 int begin_call(adsb_ctx *ctx, long long n_tiles, long long n_out, cudaStream_t s)
 {
-    init_header_kernel<<<1, 1, 0, s>>>(ctx->d_hdr);
+    ADSB_LAUNCH(init_header_kernel, 1, 1, 0, s, ctx->d_hdr);
     CK(cudaGetLastError());
     size_t n = (size_t)(n_tiles / kTilesPerChunk) + 2;
     if (n > ctx->tile_chunk_n) n = ctx->tile_chunk_n;
@@ -681,7 +681,7 @@ int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int wor
     if (!ctx || !ctx->last.pending || !d_gathered || world < 1 || rank < 0 || rank >= world) return ADSB_E_INVAL;
     ON_DEVICE(ctx);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
-    carry_plan_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, reinterpret_cast<const long long *>(d_gathered), world, rank,
+    ADSB_LAUNCH(carry_plan_kernel, 1, 1, 0, s, ctx->d_hdr, reinterpret_cast<const long long *>(d_gathered), world, rank,
                                       63LL * ctx->sps, final_check);
     CK(cudaGetLastError());
     if (final_check) return ADSB_OK;
@@ -696,7 +696,7 @@ int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_o
     if (!ctx || !ctx->last.pending || !d_out3) return ADSB_E_INVAL;
     ON_DEVICE(ctx);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->last.stream;
-    export_carry_kernel<<<1, 1, 0, s>>>(ctx->d_hdr, ctx->last.base, used_global, used_global == ADSB_CARRY_USED_ON_DEVICE,
+    ADSB_LAUNCH(export_carry_kernel, 1, 1, 0, s, ctx->d_hdr, ctx->last.base, used_global, used_global == ADSB_CARRY_USED_ON_DEVICE,
                                         reinterpret_cast<long long *>(d_out3));
     CK(cudaGetLastError());
     return ADSB_OK;
@@ -821,9 +821,9 @@ int adsb_burst_mag_out(adsb_ctx *ctx, float *out, size_t n_out)
     const size_t max_blocks = (size_t)ctx->num_sms * 8;
     const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
     switch (ctx->staged_fmt) {
-    case kFmtC64: mag_out_kernel<kFmtC64><<<blocks, kThreads, 0, s>>>(ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
-    case kFmtSC16: mag_out_kernel<kFmtSC16><<<blocks, kThreads, 0, s>>>(ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
-    default: mag_out_kernel<kFmtF32><<<blocks, kThreads, 0, s>>>(ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    case kFmtC64: ADSB_LAUNCH(mag_out_kernel<kFmtC64>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    case kFmtSC16: ADSB_LAUNCH(mag_out_kernel<kFmtSC16>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    default: ADSB_LAUNCH(mag_out_kernel<kFmtF32>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, ctx->d_mag, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -921,7 +921,7 @@ int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *so
     CK(cudaMemcpyAsync(ctx->d_sob, sob_idx, n_tags * sizeof(long long), cudaMemcpyHostToDevice, s));
     unsigned blocks = (unsigned)((n_tags + kWarps - 1) / kWarps);
     if (blocks > (unsigned)ctx->num_sms * 8u) blocks = (unsigned)ctx->num_sms * 8u;
-    demod_kernel<<<blocks, kThreads, 0, s>>>((const float *)ctx->d_in, (long long)n, ctx->d_sob, (int)n_tags, ctx->sps,
+    ADSB_LAUNCH(demod_kernel, blocks, kThreads, 0, s, (const float *)ctx->d_in, (long long)n, ctx->d_sob, (int)n_tags, ctx->sps,
                                              ctx->d_bits, ctx->d_valid);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(valid, ctx->d_valid, n_tags, cudaMemcpyDeviceToHost, s));

@@ -10,6 +10,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Kernel launches go through one macro so that the same sources also build for the GPU-less logic tests
+// (tests/emu: every CUDA thread a host fiber; test infrastructure, never part of the shipped library).
+#if defined(ADSB_HOST_EMU)
+#define ADSB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    cuda_emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#else
+#define ADSB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace adsb {
 
 constexpr int kThreads = 256;
@@ -88,20 +97,32 @@ struct ScanParams {
 __device__ __forceinline__ float2 ldg_stream_f2(const float2 *p)
 {
     float2 v;
+#if defined(ADSB_HOST_EMU)
+    v = *p;
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+#endif
     return v;
 }
 __device__ __forceinline__ float ldg_stream_f1(const float *p)
 {
     float v;
+#if defined(ADSB_HOST_EMU)
+    v = *p;
+#else
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#endif
     return v;
 }
 
 __device__ __forceinline__ unsigned long long ldg_stream_b64(const void *p)
 {
     unsigned long long v;
+#if defined(ADSB_HOST_EMU)
+    memcpy(&v, p, 8);
+#else
     asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+#endif
     return v;
 }
 
@@ -109,11 +130,17 @@ __device__ __forceinline__ unsigned long long ldg_stream_b64(const void *p)
 // lanes round-to-nearest like two FMULs) + one add -- same value as mag2() below
 __device__ __forceinline__ float mag2_packed(unsigned long long v)
 {
+#if defined(ADSB_HOST_EMU)
+    float2 c;
+    memcpy(&c, &v, 8);
+    return __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));
+#else
     unsigned long long sq;
     asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(v));
     float a, b;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(sq));
     return __fadd_rn(a, b);
+#endif
 }
 
 // |IQ|^2 exactly as the oracle: fl32(fl32(re*re) + fl32(im*im)), no FMA contraction (adsb_rx.py:180)
@@ -138,7 +165,11 @@ __device__ __forceinline__ float mag2_sc16(unsigned v)
 __device__ __forceinline__ unsigned ldg_stream_b32(const void *p)
 {
     unsigned v;
+#if defined(ADSB_HOST_EMU)
+    memcpy(&v, p, 4);
+#else
     asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
     return v;
 }
 

@@ -393,8 +393,13 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         if (((unsigned)ta - P.fast_lo) <= P.fast_span) {
             const char *base = reinterpret_cast<const char *>(P.in) + (ta * T - kLeftHalo) * (FMT == kFmtC64 ? 8 : 4);
             constexpr int kLines = (kLeftHalo + T + G::RH) * (FMT == kFmtC64 ? 8 : 4) / 128;
+#if !defined(ADSB_HOST_EMU)
             for (int l = tid; l < kLines; l += kThreads)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
+#else
+            (void)base;
+            (void)kLines;
+#endif
         }
     }
     if (fast) {
@@ -840,7 +845,11 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
 template <int SPS, int FMT>
 __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) scan_slice_kernel(const ScanParams P)
 {
+#if defined(ADSB_HOST_EMU)
+    unsigned char *smem_raw = cuda_emu::dynamic_smem();
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     const TileSmem sm = carve(smem_raw, Geo<SPS>::T, SPS ? Geo<SPS>::RH : P.rh);
     const long long tile = (long long)P.tile_first + blockIdx.x;
     const CtaBar gb;

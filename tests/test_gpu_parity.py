@@ -4,6 +4,8 @@ and with the oracle.  Bit-exact for tag offsets, PDU order and bits, carried sta
 import numpy as np
 import pytest
 
+import devmem
+
 import golden_io as G
 import gr_adsb_b200 as g
 from gr_adsb_b200 import synth
@@ -153,12 +155,12 @@ def test_device_resident_entry_point():
     n, sps, thr = 1 << 20, 2, 0.01
     d = synth.synth_numpy(n, sps=sps, n_bursts=2000, seed=77)
     ref = co.run_stream(co.mag2(d["iq"]), sps * 1e6, thr, None)
-    t = torch.from_numpy(d["iq"].view(np.float32).reshape(-1, 2)).cuda()
+    t = devmem.to_dev(torch.from_numpy(d["iq"].view(np.float32).reshape(-1, 2)))
     ctx = ctx_for(sps, n)
-    s = torch.cuda.current_stream().cuda_stream
+    s = devmem.stream()
     for _ in range(2):          # second call re-uses every buffer (epoch handling)
         ctx.burst_work_dev(t.data_ptr(), 1, n, n, 8 * sps - 1, thr, base=0, eob_in=-1, stream=s)
-        torch.cuda.synchronize()
+        devmem.sync()
         cnt, hits = ctx.burst_finish(cap=len(ref["tag_off"]) + 8)
         crc = np.array([co.crc_pass(b) for b in ref["pdu_bits"]], np.uint8)
         check_fused(hits, sps, ref["tag_off"], ref["tag_snr"], ref["pdu_off"], ref["pdu_bits"], crc)
@@ -171,15 +173,15 @@ def test_full_size_properties():
     its neighbours must come back with exactly its bits and a passing CRC; hits are ordered and obey
     the 63-symbol blanking; all of it twice (determinism)."""
     torch = pytest.importorskip("torch")
-    n, sps, thr = 1 << 26, 2, 0.01
+    n, sps, thr = 1 << (21 if devmem.EMU else 26), 2, 0.01      # the emulation runs ~0.4 Msamples/s
     nb = int(n * 5e-3)
-    iq, truth = synth.synth_torch(n, sps, nb, 20260925, "cuda")
+    iq, truth = synth.synth_torch(n, sps, nb, 20260925, devmem.DEVICE)
     ctx = g.Context(sps, n)
-    s = torch.cuda.current_stream().cuda_stream
+    s = devmem.stream()
     outs = []
     for _ in range(2):
         ctx.burst_work_dev(iq.data_ptr(), 1, n, n, 8 * sps - 1, thr, stream=s)
-        torch.cuda.synchronize()
+        devmem.sync()
         cnt, hits = ctx.burst_finish(cap=n // 126 + 8)
         outs.append((cnt, hits.copy()))
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])

@@ -5,6 +5,8 @@ whole-buffer oracle."""
 import numpy as np
 import pytest
 
+import devmem
+
 import gr_adsb_b200 as g
 from gr_adsb_b200 import sharding, synth
 from oracle import c_oracle as co
@@ -17,7 +19,7 @@ def run_sharded(iq, sps, thr, world):
     n = len(iq)
     L = n // world
     assert L * world == n
-    full = torch.from_numpy(iq.view(np.float32).reshape(-1, 2)).cuda()
+    full = devmem.to_dev(torch.from_numpy(iq.view(np.float32).reshape(-1, 2)))
     geos = [sharding.shard_geometry(r, world, L, sps) for r in range(world)]
     ctxs = [g.Context(sps, geo["n_in"]) for geo in geos]
     bufs = []
@@ -26,14 +28,14 @@ def run_sharded(iq, sps, thr, world):
         hi = (r + 1) * L + geo["right"]
         bufs.append(full[lo:hi].contiguous())          # what exchange_halos assembles on rank r
         assert bufs[-1].shape[0] == geo["n_in"]
-    s = torch.cuda.current_stream().cuda_stream
+    s = devmem.stream()
     used = [sharding.NONE] * world
     for r, geo in enumerate(geos):
         ctxs[r].burst_work_dev(bufs[r].data_ptr(), 1, geo["n_in"], geo["n_out"], geo["lead"], thr,
                                base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=s)
     rounds = reruns = 0
     while True:
-        torch.cuda.synchronize()
+        devmem.sync()
         infos = []
         for r, geo in enumerate(geos):
             c, _ = ctxs[r].burst_finish(fetch_hits=False)
@@ -102,12 +104,12 @@ def run_sharded_device_carry(iq, sps, thr, world):
     torch = pytest.importorskip("torch")
     n = len(iq)
     L = n // world
-    full = torch.from_numpy(iq.view(np.float32).reshape(-1, 2)).cuda()
+    full = devmem.to_dev(torch.from_numpy(iq.view(np.float32).reshape(-1, 2)))
     geos = [sharding.shard_geometry(r, world, L, sps) for r in range(world)]
     ctxs = [g.Context(sps, geo["n_in"]) for geo in geos]
     bufs = [full[r * L - geo["left"]: (r + 1) * L + geo["right"]].contiguous() for r, geo in enumerate(geos)]
-    s = torch.cuda.current_stream().cuda_stream
-    gathered = torch.zeros(3 * world, dtype=torch.int64, device="cuda")
+    s = devmem.stream()
+    gathered = torch.zeros(3 * world, dtype=torch.int64, device=devmem.DEVICE)
     for r, geo in enumerate(geos):
         ctxs[r].burst_work_dev(bufs[r].data_ptr(), 1, geo["n_in"], geo["n_out"], geo["lead"], thr,
                                base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=s)
@@ -119,7 +121,7 @@ def run_sharded_device_carry(iq, sps, thr, world):
                 ctxs[r].burst_export_carry_dev(g.CARRY_USED_ON_DEVICE, gathered.data_ptr() + 24 * r, stream=s)
             for r in range(world):
                 ctxs[r].burst_carry_round_dev(gathered.data_ptr(), world, r, final_check=final, stream=s)
-        torch.cuda.synchronize()
+        devmem.sync()
         rounds += 1
         now = [ctxs[r].burst_finish(fetch_hits=False)[0]["carry_unstable"] for r in range(world)]
         settled = now == seen
