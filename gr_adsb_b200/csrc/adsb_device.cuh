@@ -308,6 +308,68 @@ __device__ __forceinline__ void half_sort128(unsigned (&k)[8], int lane)
     }
 }
 
+// The two middle order statistics (ranks 63 and 64 of 128) of each half-warp's 128 keys, without finishing the
+// sort: sort the two 64-key halves A (lanes 0-7) and B (lanes 8-15) as half_sort128 does, then use that
+// {min(A[i], B[63-i])} are exactly the 64 smallest keys and {max(A[i], B[63-i])} the 64 largest -- rank 63 is the
+// largest of the former, rank 64 the smallest of the latter.  Replaces the last 7 of 28 network steps by one
+// exchange and two reductions.  `top` = the largest key (last element of A or of B).
+__device__ __forceinline__ void half_mid128(unsigned (&k)[8], int lane, unsigned &lo_mid, unsigned &hi_mid, unsigned &top)
+{
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
+    cex(k[0], k[3]); cex(k[1], k[2]); cex(k[4], k[7]); cex(k[5], k[6]);
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
+    cex(k[0], k[7]); cex(k[1], k[6]); cex(k[2], k[5]); cex(k[3], k[4]);
+    cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
+#pragma unroll
+    for (int size = 16; size <= 64; size <<= 1) {
+        {
+            const int lm = (size >> 3) - 1;
+            const bool lower = (lane & (size >> 4)) == 0;
+            unsigned o[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) o[r] = __shfl_xor_sync(kFull, k[7 - r], lm);
+#pragma unroll
+            for (int r = 0; r < 8; r++) k[r] = lower ? min(k[r], o[r]) : max(k[r], o[r]);
+        }
+#pragma unroll
+        for (int j = size >> 2; j >= 8; j >>= 1) {
+            const int lm = j >> 3;
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const unsigned o = __shfl_xor_sync(kFull, k[r], lm);
+                k[r] = lower ? min(k[r], o) : max(k[r], o);
+            }
+        }
+        cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
+        cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
+    }
+    // A = positions 0..63 (lanes 0-7 of the half-warp), B = 64..127 (lanes 8-15), both ascending
+    const unsigned ta = __shfl_sync(kFull, k[7], (lane & 16) | 7), tb = __shfl_sync(kFull, k[7], (lane & 16) | 15);
+    top = max(ta, tb);
+    const bool lower = (lane & 8) == 0;
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const unsigned o = __shfl_xor_sync(kFull, k[7 - r], 15);       // position e <-> 127 - e
+        const unsigned v = lower ? min(k[r], o) : max(k[r], o);
+        m = (r == 0) ? v : (lower ? max(m, v) : min(m, v));
+    }
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+        const unsigned o = __shfl_xor_sync(kFull, m, d);
+        m = lower ? max(m, o) : min(m, o);
+    }
+    lo_mid = __shfl_sync(kFull, m, lane & 16);
+    hi_mid = __shfl_sync(kFull, m, (lane & 16) | 8);
+}
+
 __device__ __forceinline__ unsigned pick4(const unsigned (&k)[4], int r)
 {
     unsigned v = k[0];
