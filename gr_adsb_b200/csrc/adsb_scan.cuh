@@ -26,6 +26,9 @@ namespace adsb {
 #ifndef ADSB_OPT_PREFETCH_OWN
 #define ADSB_OPT_PREFETCH_OWN 0  // L2 prefetch covers the target tile's own samples only (0: its halos as well)
 #endif
+#ifndef ADSB_OPT_PREFILTER_SIGN
+#define ADSB_OPT_PREFILTER_SIGN 0  // dense pre-filter compares through the sign of a subtraction (complex / sc16 input)
+#endif
 #ifndef ADSB_LMAX2
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
@@ -155,6 +158,17 @@ __device__ __forceinline__ bool preamble_match_rest(const float *m)
     for (int k = 10; k < 16; k++)
         if (m[k * HS] > half) return false;
     return xp > half;
+}
+
+// a > b as a word whose SIGN BIT is the answer, for a, b that are +0, positive, +inf or the canonical NaN (see the
+// dense pre-filter).  The host emulation compares directly: x86 gives inf - inf and propagated NaNs a sign bit.
+__device__ __forceinline__ unsigned gt_sign(float a, float b)
+{
+#if defined(ADSB_HOST_EMU)
+    return (a > b) ? 0x80000000u : 0u;
+#else
+    return __float_as_uint(__fadd_rn(b, -a));
+#endif
 }
 
 __device__ __forceinline__ bool demod_in_range(const ScanParams &P, long long p)
@@ -585,13 +599,32 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     vals[4 * q] = t.x; vals[4 * q + 1] = t.y; vals[4 * q + 2] = t.z; vals[4 * q + 3] = t.w;
                 }
                 unsigned Q = 0;
+#if ADSB_OPT_PREFILTER_SIGN
+                if (FMT != kFmtF32) {
+                    // |IQ|^2 computed in phase 1 is +0, positive, +inf or the canonical NaN 0x7fffffff, for which
+                    // `m3 > half` is exactly the sign bit of fl32(half - m3): distinct finite values never subtract
+                    // to zero (no flush-to-zero here), inf - inf and anything with a NaN give the sign-less canonical
+                    // NaN.  One FADD (FMA pipe) and one funnel shift replace FSETP + SEL + ADD, all three on the ALU pipe
+                    // this kernel loads most.  (float32 input may hold -0.0 or negative values: compare as before.)
 #pragma unroll
-                for (int j = 0; j < 15 + G::DB; j++) {
-                    const int i0 = 4 - G::DB + j;                 // index of position k0 - DB + j in vals
-                    const float half = __fmul_rn(vals[i0], 0.5f);
-                    // none of the three taps may exceed half (NaN taps count as low, like `tap > half`)
-                    const float m3 = fmaxf(fmaxf(vals[i0 + 3 * G::H], vals[i0 + 4 * G::H]), vals[i0 + 5 * G::H]);
-                    Q |= !(m3 > half) ? (1u << (16 - G::DB + j)) : 0u;
+                    for (int j = 14 + G::DB; j >= 0; j--) {
+                        const int i0 = 4 - G::DB + j;
+                        const float half = __fmul_rn(vals[i0], 0.5f);
+                        const float m3 = fmaxf(fmaxf(vals[i0 + 3 * G::H], vals[i0 + 4 * G::H]), vals[i0 + 5 * G::H]);
+                        Q = __funnelshift_l(gt_sign(m3, half), Q, 1);        // Q = Q << 1 | (m3 > half)
+                    }
+                    Q = ~Q << (16 - G::DB);               // bit 16 - DB + j <-> position j (bit 31 is junk; C never has it)
+                } else
+#endif
+                {
+#pragma unroll
+                    for (int j = 0; j < 15 + G::DB; j++) {
+                        const int i0 = 4 - G::DB + j;                 // index of position k0 - DB + j in vals
+                        const float half = __fmul_rn(vals[i0], 0.5f);
+                        // none of the three taps may exceed half (NaN taps count as low, like `tap > half`)
+                        const float m3 = fmaxf(fmaxf(vals[i0 + 3 * G::H], vals[i0 + 4 * G::H]), vals[i0 + 5 * G::H]);
+                        Q |= !(m3 > half) ? (1u << (16 - G::DB + j)) : 0u;
+                    }
                 }
                 unsigned Tm = C & Q;
                 while (Tm) {
