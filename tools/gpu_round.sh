@@ -9,7 +9,7 @@ T0=$(date +%s)
 el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
 el start
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv,noheader
-timeout 170 python tools/variant_check.py run --variants base,allsgn,all --iters 30 > gpurun_out/variants.log 2>&1
+timeout 170 python tools/variant_check.py run --variants base,midsgn,midsgnpf,midsgnpflate,midsgnpfwl,wl,late --iters 30 > gpurun_out/variants.log 2>&1
 el "variants rc=$?"
 BEST=$(cat gpurun_out/best_variant.txt 2>/dev/null || echo base)
 export ADSB_B200_LIB=$PWD/gr_adsb_b200/csrc/variants/libadsb_$BEST.so
@@ -22,5 +22,3 @@ timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 el "ncu list rc=$?"
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:scan_slice -s 6 -c 1 -f -o gpurun_out/scan_best python bench.py --steps 4 --warmup 2 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
 el "ncu full rc=$?"
-timeout 110 python tools/variant_check.py run --variants w0,mid,sgn --iters 30 --no-best >> gpurun_out/variants.log 2>&1
-el "variants2 rc=$?"

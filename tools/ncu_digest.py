@@ -11,7 +11,7 @@ import sys
 
 rep, kern = sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "scan_slice_kernelILi2ELb1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(ROOT, "gr_adsb_b200", "csrc", "libadsb_b200.so")
+lib = os.environ.get("ADSB_B200_LIB", os.path.join(ROOT, "gr_adsb_b200", "csrc", "libadsb_b200.so"))   # the build the report was taken with
 
 
 def run(cmd):
