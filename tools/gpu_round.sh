@@ -9,11 +9,13 @@ T0=$(date +%s)
 el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
 el start
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv,noheader
-timeout 170 python tools/variant_check.py run --variants base,midsgn,midsgnpf,midsgnpflate,midsgnpfwl,wl,late --iters 30 > gpurun_out/variants.log 2>&1
+timeout 170 python tools/variant_check.py run --variants base,midsgn,midsgnpf,midsgnpflate,midsgnpfwl,wl,late,midsgnpf@148,midsgnpf@444 --iters 30 > gpurun_out/variants.log 2>&1
 el "variants rc=$?"
-BEST=$(cat gpurun_out/best_variant.txt 2>/dev/null || echo base)
+BESTFULL=$(cat gpurun_out/best_variant.txt 2>/dev/null || echo base)
+BEST=${BESTFULL%@*}
+if [ "$BEST" != "$BESTFULL" ]; then export ADSB_PREFETCH_TILES=${BESTFULL#*@}; fi
 export ADSB_B200_LIB=$PWD/gr_adsb_b200/csrc/variants/libadsb_$BEST.so
-el "best=$BEST"
+el "best=$BESTFULL"
 timeout 220 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_best.json 2> gpurun_out/bench_best.log
 el "bench rc=$?"
 timeout 260 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_best.log 2>&1

@@ -186,7 +186,11 @@ def run(names, log2n, iters, write_best=True):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     results = []
     for name in names:
-        env = dict(os.environ, ADSB_B200_LIB=lib_of(name))
+        # "variant@N": the same library with the L2 prefetch distance set to N tiles (ADSB_PREFETCH_TILES)
+        vname, _, pf = name.partition("@")
+        env = dict(os.environ, ADSB_B200_LIB=lib_of(vname))
+        if pf:
+            env["ADSB_PREFETCH_TILES"] = pf
         t0 = time.time()
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "one", name, str(log2n), str(iters)], env=env,
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
