@@ -265,51 +265,11 @@ __device__ __forceinline__ void warp_sort128(unsigned (&k)[4], int lane)
     }
 }
 
-// Two independent 128-key sorts per warp: lanes 0-15 sort one set, lanes 16-31 another; 8 keys per lane,
-// logical position e = 8*(lane & 15) + r, ascending, same mirrored network.  Only 10 of the 28 steps
-// cross lanes (15 in the 4-keys-per-lane layout), which is what makes slicing candidates in pairs cheaper.
-__device__ __forceinline__ void half_sort128(unsigned (&k)[8], int lane)
-{
-    // sizes 2, 4, 8: entirely inside the lane
-#pragma unroll
-    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-    cex(k[0], k[3]); cex(k[1], k[2]); cex(k[4], k[7]); cex(k[5], k[6]);
-#pragma unroll
-    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-    cex(k[0], k[7]); cex(k[1], k[6]); cex(k[2], k[5]); cex(k[3], k[4]);
-    cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
-#pragma unroll
-    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-#pragma unroll
-    for (int size = 16; size <= 128; size <<= 1) {
-        {   // mirror step: e <-> e ^ (size-1): lane ^ (size/8 - 1), register 7 - r
-            const int lm = (size >> 3) - 1;
-            const bool lower = (lane & (size >> 4)) == 0;
-            unsigned o[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) o[r] = __shfl_xor_sync(kFull, k[7 - r], lm);
-#pragma unroll
-            for (int r = 0; r < 8; r++) k[r] = lower ? min(k[r], o[r]) : max(k[r], o[r]);
-        }
-#pragma unroll
-        for (int j = size >> 2; j >= 8; j >>= 1) {
-            const int lm = j >> 3;
-            const bool lower = (lane & lm) == 0;
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const unsigned o = __shfl_xor_sync(kFull, k[r], lm);
-                k[r] = lower ? min(k[r], o) : max(k[r], o);
-            }
-        }
-        cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
-        cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
-#pragma unroll
-        for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-    }
-}
-
-// The two middle order statistics (ranks 63 and 64 of 128) of each half-warp's 128 keys, without finishing the
-// sort: sort the two 64-key halves A (lanes 0-7) and B (lanes 8-15) as half_sort128 does, then use that
+// Two independent 128-key sets per warp: lanes 0-15 hold one, lanes 16-31 the other; 8 keys per lane, logical
+// position e = 8*(lane & 15) + r, same mirrored bitonic network as warp_sort128 (only the steps with a stride of 8
+// or more cross lanes, which is what makes slicing candidates in pairs cheaper than one per warp).
+// The two middle order statistics (ranks 63 and 64 of 128) of each set, without finishing the sort: sort the two
+// 64-key halves A (lanes 0-7) and B (lanes 8-15) with sizes 2..64 of the network, then use that
 // {min(A[i], B[63-i])} are exactly the 64 smallest keys and {max(A[i], B[63-i])} the 64 largest -- rank 63 is the
 // largest of the former, rank 64 the smallest of the latter.  Replaces the last 7 of 28 network steps by one
 // exchange and two reductions.  `top` = the largest key (last element of A or of B).

@@ -17,24 +17,6 @@ namespace adsb {
 #ifndef ADSB_MIN_CTAS_BIG
 #define ADSB_MIN_CTAS_BIG 4  // same for the 8192-sample tile kernels (8 Msps and unspecialised rates)
 #endif
-#ifndef ADSB_OPT_COMPACT_W0
-#define ADSB_OPT_COMPACT_W0 0  // per-tile candidate list built by warp 0 from per-chunk masks (0: block-wide scan)
-#endif
-#ifndef ADSB_OPT_MEDIAN_MID
-#define ADSB_OPT_MEDIAN_MID 0  // noise median from the two middle order statistics of a half-finished sort (0: full sort)
-#endif
-#ifndef ADSB_OPT_PREFETCH_OWN
-#define ADSB_OPT_PREFETCH_OWN 0  // L2 prefetch covers the target tile's own samples only (0: its halos as well)
-#endif
-#ifndef ADSB_OPT_PREFILTER_SIGN
-#define ADSB_OPT_PREFILTER_SIGN 0  // dense pre-filter compares through the sign of a subtraction (complex / sc16 input)
-#endif
-#ifndef ADSB_OPT_LATE_HEADER
-#define ADSB_OPT_LATE_HEADER 0  // tile bookkeeping (flags, last pulse, tile table) published after the pre-slice barrier
-#endif
-#ifndef ADSB_OPT_WARP_LISTS
-#define ADSB_OPT_WARP_LISTS 0  // per-warp candidate lists: one barrier between detection and slicing (needs COMPACT_W0 = 0)
-#endif
 #ifndef ADSB_LMAX2
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
@@ -64,7 +46,6 @@ __host__ __device__ inline int right_halo(int sps)
 #define ADSB_MIN_CTAS 8      // resident CTAs per SM the 4096-sample tile kernels are compiled for
 #endif
 constexpr int kTileSlots = 32;    // candidate records reserved per tile (typical busy tile: 5-10)
-constexpr int kSegCap = 256;      // entries per (warp, chunk row) segment of the tile's candidate list (ADSB_OPT_WARP_LISTS)
 constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
 
 // ---- shared-memory layout ------------------------------------------------------------------------
@@ -74,7 +55,6 @@ struct TileSmem {
     unsigned short *list;   // T/2 + 2
     unsigned short *xmask;  // T/16   extra candidate bits (by fall position) from the long-run pass
     unsigned short *xlong;  // T/16   which of them are long-run entries
-    unsigned *cl;           // T/16   (same storage as xmask+xlong) per chunk: candidate bits | long-run bits << 16
     unsigned short *slow;   // kSlowCap fall slots
     int *scratch;           // 64 ints: slots below + per-warp reduction cells
 };
@@ -104,7 +84,6 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
     s.list = reinterpret_cast<unsigned short *>(raw);
     raw += align16(((size_t)T / 2 + 2) * 2);
     s.xmask = reinterpret_cast<unsigned short *>(raw);
-    s.cl = reinterpret_cast<unsigned *>(raw);
     raw += align16((size_t)(T / 16) * 2);
     s.xlong = reinterpret_cast<unsigned short *>(raw);
     raw += align16((size_t)(T / 16) * 2);
@@ -336,7 +315,6 @@ __device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float 
     const int hl = lane & 15;
     unsigned k[8];
     bool nan = false;
-#if ADSB_OPT_MEDIAN_MID
     // 100 samples + 14 pads below everything + 14 pads above everything: the median's two order statistics
     // (ranks 49, 50 of 100) are ranks 63, 64 of the 128, the two middle ones
     constexpr int kLowPads = (128 - kNoise) / 2;
@@ -363,33 +341,6 @@ __device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float 
         med = __fmul_rn(__fadd_rn(key2f(ka), key2f(kb)), 0.5f);
         if ((anyn >> (lane & 16)) & 0xffffu) med = __int_as_float(0x7fc00000);
     }
-#else
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int e = r * 16 + hl;
-        const float v = (e < kNoise) ? mp[e - kNoise] : 0.0f;
-        if (FMT != kFmtF32) {
-            // |IQ|^2 computed here is never negative: the raw bits order like the values; NaN bits sort above +inf
-            k[r] = (e < kNoise) ? __float_as_uint(v) : 0x7f800000u;
-        } else {
-            nan |= (e < kNoise) && (v != v);
-            k[r] = (e < kNoise) ? f2key(v) : 0xffffffffu;
-        }
-    }
-    half_sort128(k, lane);
-    const int src = (lane & 16) | 6;                       // ranks 49, 50 -> position 8*6 + 1, 8*6 + 2
-    const unsigned ka = __shfl_sync(kFull, k[1], src), kb = __shfl_sync(kFull, k[2], src);
-    float med;
-    if (FMT != kFmtF32) {
-        const unsigned top = __shfl_sync(kFull, k[7], (lane & 16) | 15);
-        med = __fmul_rn(__fadd_rn(__uint_as_float(ka), __uint_as_float(kb)), 0.5f);   // fl32(fl32(a+b)/2)
-        if (top > 0x7f800000u) med = __int_as_float(0x7fc00000);
-    } else {
-        const unsigned anyn = __ballot_sync(kFull, nan);
-        med = __fmul_rn(__fadd_rn(key2f(ka), key2f(kb)), 0.5f);
-        if ((anyn >> (lane & 16)) & 0xffffu) med = __int_as_float(0x7fc00000);
-    }
-#endif
     if (write && hl == 0) {
         rec.idx = P.base + p;
         rec.snr = __fdiv_rn(mp[0], med);       // ratio; the compact kernel applies 10*log10(.)+1.6
@@ -442,9 +393,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 
     if (tid == 0) {
         sm.scratch[kScrSlowN] = 0;
-#if ADSB_OPT_WARP_LISTS
-        *reinterpret_cast<long long *>(sm.scratch + kScrMaxLong) = -1;
-#endif
     }
     const long long a0 = tile * T;                 // array index of the tile's first owned sample
     const long long w0 = a0 + P.lead - kLeftHalo;  // window index of shared-memory slot 0
@@ -457,15 +405,10 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         // gets to it, its loads are L2 hits instead of HBM round trips
         const long long ta = tile + P.prefetch_tiles;
         if (((unsigned)ta - P.fast_lo) <= P.fast_span) {
-#if ADSB_OPT_PREFETCH_OWN
             // only that tile's own T samples: its halos are the neighbouring tiles' own ranges, prefetched by the
             // CTAs that run next to this one; T * itemsize / 128 lines = one per thread for complex64 at T = 4096
             const char *base = reinterpret_cast<const char *>(P.in) + ta * T * (FMT == kFmtC64 ? 8 : 4);
             constexpr int kLines = T * (FMT == kFmtC64 ? 8 : 4) / 128;
-#else
-            const char *base = reinterpret_cast<const char *>(P.in) + (ta * T - kLeftHalo) * (FMT == kFmtC64 ? 8 : 4);
-            constexpr int kLines = (kLeftHalo + T + G::RH) * (FMT == kFmtC64 ? 8 : 4) / 128;
-#endif
 #if !defined(ADSB_HOST_EMU)
 #pragma unroll
             for (int l = tid; l < kLines; l += kThreads)
@@ -611,7 +554,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     vals[4 * q] = t.x; vals[4 * q + 1] = t.y; vals[4 * q + 2] = t.z; vals[4 * q + 3] = t.w;
                 }
                 unsigned Q = 0;
-#if ADSB_OPT_PREFILTER_SIGN
                 if (FMT != kFmtF32) {
                     // |IQ|^2 computed in phase 1 is +0, positive, +inf or the canonical NaN 0x7fffffff, for which
                     // `m3 > half` is exactly the sign bit of fl32(half - m3): distinct finite values never subtract
@@ -627,7 +569,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     }
                     Q = ~Q << (16 - G::DB);               // bit 16 - DB + j <-> position j (bit 31 is junk; C never has it)
                 } else
-#endif
                 {
 #pragma unroll
                     for (int j = 0; j < 15 + G::DB; j++) {
@@ -695,267 +636,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         lmask[ci] = lm;
     }
 
-#if ADSB_OPT_COMPACT_W0 && ADSB_OPT_WARP_LISTS
-#error "ADSB_OPT_COMPACT_W0 and ADSB_OPT_WARP_LISTS are alternatives"
-#endif
-#if ADSB_OPT_COMPACT_W0
-    // ---- candidate masks, edge flags, last pulse -> shared memory; the barrier that publishes them also tells
-    // whether any run was deferred (rare) ----
-#pragma unroll
-    for (int ci = 0; ci < NCH; ci++) {
-        const int c = tid + ci * kThreads;
-        if (c < T / 16) sm.cl[c] = cmask[ci] | (lmask[ci] << 16);     // low half: candidates by fall bit, high: long-run entries
-    }
-    int *s_max = sm.scratch + kScrMax;
-    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + kScrFlag);
-    {
-        const unsigned f = __reduce_or_sync(kFull, tflags);
-        const int m = __reduce_max_sync(kFull, tmax);
-        if (lane == 0) {
-            s_flag[wid] = f;
-            s_max[wid] = m;
-        }
-    }
-
-    // ---- long runs (rare): one warp per deferred fall; matches are OR-ed into the chunk masks ----
-    long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + kScrMaxLong);
-    if (gb.sync_or(have_long)) {
-        if (tid == 0) s_max_long = -1;
-        gb.sync();
-        const int n_slow = sm.scratch[kScrSlowN];
-        const Access<FMT> X{P, sm.mag, w0, S};
-        if (n_slow <= kSlowCap) {
-            for (int e = wid; e < n_slow; e += kWarps) {
-                const int kf = sm.slow[e];
-                long long p;
-                if (!resolve_long<FMT>(P, sm, w0, kf, lane, p)) continue;
-                const bool m = warp_match<FMT>(X, p, h, lane);
-                if (lane == 0) {
-                    atomicMax(&s_max_long, p);
-                    if (m) atomicOr(&sm.cl[(kf - kLeftHalo) >> 4], 0x10001u << ((kf - kLeftHalo) & 15));
-                }
-            }
-        } else {
-            // more long runs than the deferral list holds: every warp rescans its own chunks
-            for (int c = wid; c < T / 16; c += kWarps) {
-                const int wq = kLeftHalo / 32 + (c >> 1);
-                const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
-                const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
-                unsigned F = ~W & (W << 1) & 0xffff0000u;
-                const int k0 = kLeftHalo + c * 16;
-                const long long i0 = w0 + k0;
-                long long lo = P.own_lo - i0, hi = P.own_hi - i0;
-                lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
-                hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
-                F &= (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << 16) : 0u;
-                unsigned fm = F >> 16;
-                while (fm) {
-                    const int b = __ffs(fm) - 1;
-                    fm &= fm - 1;
-                    const int pos = 16 + b;
-                    const int run = __clz(~(W << (32 - pos)));
-                    if (fast ? (run <= G::LMAX) : (run < pos)) continue;     // handled as a short run already
-                    long long p;
-                    if (!resolve_long<FMT>(P, sm, w0, k0 + b, lane, p)) continue;
-                    const bool m = warp_match<FMT>(X, p, h, lane);
-                    if (lane == 0) {
-                        atomicMax(&s_max_long, p);
-                        if (m) atomicOr(&sm.cl[c], 0x10001u << b);
-                    }
-                }
-            }
-        }
-        gb.sync();
-    } else if (tid == 0) {
-        s_max_long = -1;
-    }
-
-    // ---- ordered compaction of the tile's candidates into sm.list, by warp 0 alone: a lane owns CPL consecutive
-    // chunks, one warp scan orders the lanes.  (Candidates are rare -- a handful per tile -- so seven warps
-    // skipping this costs less than all eight taking part in a block-wide scan.) ----
-    if (wid == 0) {
-        constexpr int CPL = T / 16 / 32;
-        unsigned m[CPL];
-        int cnt = 0;
-#pragma unroll
-        for (int q = 0; q < CPL; q += 4) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(sm.cl + lane * CPL + q);
-            m[q] = v.x; m[q + 1] = v.y; m[q + 2] = v.z; m[q + 3] = v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < CPL; q++) cnt += __popc(m[q] & 0xffffu);
-        int inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(kFull, inc, d);
-            if (lane >= d) inc += t;
-        }
-        const int n_cand = __shfl_sync(kFull, inc, 31);
-        if (cnt) {
-            int off = inc - cnt;
-#pragma unroll 1
-            for (int q = 0; q < CPL; q++) {
-                const unsigned mq = sm.cl[lane * CPL + q];      // re-read: keeps the rare path small
-                unsigned cm = mq & 0xffffu;
-                const unsigned lm = mq >> 16;
-                const int k0 = kLeftHalo + (lane * CPL + q) * 16;
-                while (cm) {
-                    const int b = __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    const int kf = k0 + b;
-                    unsigned short ent = (unsigned short)(kf | 0x8000);
-                    if (!((lm >> b) & 1u)) {
-                        const int r = walk_back_smem(sm.bits, kf);       // >= 0: resolved in-thread above
-                        ent = (unsigned short)((r + kf) >> 1);
-                    }
-                    sm.list[off++] = ent;
-                }
-            }
-        }
-        if (lane == 0) {
-            unsigned ff = 0;
-            int mi = -1;
-#pragma unroll
-            for (int q = 0; q < kWarps; q++) {
-                ff |= s_flag[q];
-                mi = s_max[q] > mi ? s_max[q] : mi;
-            }
-            long long mm = (mi >= 0) ? (w0 + mi) : -1;
-            mm = s_max_long > mm ? s_max_long : mm;
-            if (ff) atomicOr(&P.hdr->flags, ff);
-            if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
-            // candidate records: a fixed block of kTileSlots per tile (no atomic round trip on the tile's critical
-            // path); the rare tile with more takes space from the overflow area behind the blocks
-            unsigned off = (unsigned)tile * kTileSlots;
-            if (n_cand > kTileSlots)
-                off = (unsigned)P.n_tiles_total * kTileSlots + (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
-            P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
-            if (n_cand > 0) atomicAdd(&P.tile_chunk_tot[tile / kThreads], (unsigned)n_cand);   // gather_kernel's chunks
-            sm.scratch[kScrOff] = (int)off;
-            sm.scratch[kScrNCand] = n_cand;
-            sm.scratch[kScrFast] = fast ? 1 : 0;
-            // x[n_out - 1] for the carried prev_in0 (framer.py:87)
-            const long long kl = (P.own_hi - 1) - w0;
-            if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
-        }
-    }
-#elif ADSB_OPT_WARP_LISTS
-    // ---- every warp lists its own candidates in its own segment of sm.list (one segment per warp and chunk row), so
-    // no warp needs another warp's count to place its entries and ONE barrier separates detection from slicing; the
-    // slicers map a tile-wide candidate index to (segment, slot) from the 8 (16) segment counts ----
-    int (*s_cnt)[kWarps] = reinterpret_cast<int (*)[kWarps]>(sm.scratch + kScrCnt);
-    int *s_max = sm.scratch + kScrMax;
-    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + kScrFlag);
-    auto list_own = [&]() {
-#pragma unroll
-        for (int ci = 0; ci < NCH; ci++) {
-            const int cnt = __popc(cmask[ci]);
-            const int wt = __reduce_add_sync(kFull, cnt);
-            if (lane == 0) s_cnt[ci][wid] = wt;
-            if (wt) {
-                int inc = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(kFull, inc, d);
-                    if (lane >= d) inc += t;
-                }
-                int off = (ci * kWarps + wid) * kSegCap + inc - cnt;
-                unsigned cm = cmask[ci];
-                const int k0 = kLeftHalo + (tid + ci * kThreads) * 16;
-                while (cm) {
-                    const int b = __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    const int kf = k0 + b;
-                    unsigned short ent = (unsigned short)(kf | 0x8000);
-                    if (!((lmask[ci] >> b) & 1u)) {
-                        const int r = walk_back_smem(sm.bits, kf);       // >= 0: resolved in-thread above
-                        ent = (unsigned short)((r + kf) >> 1);
-                    }
-                    sm.list[off++] = ent;
-                }
-            }
-        }
-    };
-    list_own();
-    {
-        const unsigned f = __reduce_or_sync(kFull, tflags);
-        const int m = __reduce_max_sync(kFull, tmax);
-        if (lane == 0) {
-            s_flag[wid] = f;
-            s_max[wid] = m;
-        }
-    }
-    long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + kScrMaxLong);     // -1 since the top of scan_tile
-    if (gb.sync_or(have_long)) {
-        // long runs (rare): one warp per deferred fall, then the lists are rebuilt
-        for (int c = tid; c < T / 16; c += kThreads) {
-            sm.xmask[c] = 0;
-            sm.xlong[c] = 0;
-        }
-        gb.sync();
-        const int n_slow = sm.scratch[kScrSlowN];
-        const Access<FMT> X{P, sm.mag, w0, S};
-        if (n_slow <= kSlowCap) {
-            for (int e = wid; e < n_slow; e += kWarps) {
-                const int kf = sm.slow[e];
-                long long p;
-                if (!resolve_long<FMT>(P, sm, w0, kf, lane, p)) continue;
-                const bool m = warp_match<FMT>(X, p, h, lane);
-                if (lane == 0) {
-                    atomicMax(&s_max_long, p);
-                    if (m) {
-                        const int c = (kf - kLeftHalo) >> 4, b = (kf - kLeftHalo) & 15;
-                        atomicOr(reinterpret_cast<unsigned *>(sm.xmask) + (c >> 1), (1u << b) << ((c & 1) * 16));
-                        atomicOr(reinterpret_cast<unsigned *>(sm.xlong) + (c >> 1), (1u << b) << ((c & 1) * 16));
-                    }
-                }
-            }
-        } else {
-            // more long runs than the deferral list holds: every warp rescans its own chunks
-            for (int c = wid; c < T / 16; c += kWarps) {
-                const int wq = kLeftHalo / 32 + (c >> 1);
-                const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
-                const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
-                unsigned F = ~W & (W << 1) & 0xffff0000u;
-                const int k0 = kLeftHalo + c * 16;
-                const long long i0 = w0 + k0;
-                long long lo = P.own_lo - i0, hi = P.own_hi - i0;
-                lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
-                hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
-                F &= (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << 16) : 0u;
-                unsigned fm = F >> 16;
-                while (fm) {
-                    const int b = __ffs(fm) - 1;
-                    fm &= fm - 1;
-                    const int pos = 16 + b;
-                    const int run = __clz(~(W << (32 - pos)));
-                    if (fast ? (run <= G::LMAX) : (run < pos)) continue;     // handled as a short run already
-                    long long p;
-                    if (!resolve_long<FMT>(P, sm, w0, k0 + b, lane, p)) continue;
-                    const bool m = warp_match<FMT>(X, p, h, lane);
-                    if (lane == 0) {
-                        atomicMax(&s_max_long, p);
-                        if (m) {
-                            atomicOr(reinterpret_cast<unsigned *>(sm.xmask) + (c >> 1), (1u << b) << ((c & 1) * 16));
-                            atomicOr(reinterpret_cast<unsigned *>(sm.xlong) + (c >> 1), (1u << b) << ((c & 1) * 16));
-                        }
-                    }
-                }
-            }
-        }
-        gb.sync();
-#pragma unroll
-        for (int ci = 0; ci < NCH; ci++) {
-            const int c = tid + ci * kThreads;
-            if (c < T / 16) {
-                cmask[ci] |= sm.xmask[c];
-                lmask[ci] |= sm.xlong[c];
-            }
-        }
-        list_own();
-        gb.sync();
-    }
-#else
     // ---- per-warp candidate counts, edge flags, last pulse -> shared memory; the barrier that publishes them
     // also tells whether any run was deferred (rare), in which case the counts are redone after that pass ----
     int (*s_cnt)[kWarps] = reinterpret_cast<int (*)[kWarps]>(sm.scratch + kScrCnt);
@@ -1102,18 +782,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         for (int ci = 0; ci < NCH; ci++) v += (lane < kWarps) ? s_cnt[ci][lane] : 0;
         n_cand = __reduce_add_sync(kFull, v);
     }
-#if ADSB_OPT_LATE_HEADER
-    // only what the slicers need goes out before the barrier; the tile's global bookkeeping (flags, last pulse, tile
-    // table, x_last) is published after it by publish_tile(), off the path the other seven warps wait on
-    if (tid == 0) {
-        unsigned off = (unsigned)tile * kTileSlots;
-        if (n_cand > kTileSlots)
-            off = (unsigned)P.n_tiles_total * kTileSlots + (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
-        sm.scratch[kScrOff] = (int)off;
-        sm.scratch[kScrNCand] = n_cand;
-        sm.scratch[kScrFast] = fast ? 1 : 0;
-    }
-#else
     if (tid == 0) {
         unsigned ff = 0;
         int mi = -1;
@@ -1140,36 +808,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         const long long kl = (P.own_hi - 1) - w0;
         if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
     }
-#endif
-#endif
-}
-
-// ---- global bookkeeping of one tile, by ONE thread after the barrier that ends scan_tile (ADSB_OPT_LATE_HEADER) ----
-template <int SPS>
-__device__ __forceinline__ void publish_tile(const ScanParams &P, const TileSmem &sm, const long long tile,
-                                             const int n_cand, const unsigned g_off)
-{
-    constexpr int T = Geo<SPS>::T;
-    const long long w0 = tile * T + P.lead - kLeftHalo;
-    const int *s_max = sm.scratch + kScrMax;
-    const unsigned *s_flag = reinterpret_cast<const unsigned *>(sm.scratch + kScrFlag);
-    const long long s_max_long = *reinterpret_cast<const long long *>(sm.scratch + kScrMaxLong);
-    unsigned ff = 0;
-    int mi = -1;
-#pragma unroll
-    for (int q = 0; q < kWarps; q++) {
-        ff |= s_flag[q];
-        mi = s_max[q] > mi ? s_max[q] : mi;
-    }
-    long long mm = (mi >= 0) ? (w0 + mi) : -1;
-    mm = s_max_long > mm ? s_max_long : mm;
-    if (ff) atomicOr(&P.hdr->flags, ff);
-    if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
-    P.tile_tab[tile] = make_uint2(g_off, (unsigned)n_cand);
-    if (n_cand > 0) atomicAdd(&P.tile_chunk_tot[tile / kThreads], (unsigned)n_cand);   // gather_kernel's chunks
-    // x[n_out - 1] for the carried prev_in0 (framer.py:87)
-    const long long kl = (P.own_hi - 1) - w0;
-    if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
 }
 
 // ---- phase 3 of one tile, by a group of n_warps warps (tid = thread index inside the group) -------------------
@@ -1184,46 +822,10 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     const int S = kLeftHalo + T + rh;
     const int h = SPS ? G::H : (P.sps >> 1);
     const long long w0 = tile * T + P.lead - kLeftHalo;
-#if ADSB_OPT_WARP_LISTS
-    // tile-wide candidate order = segments in (chunk row, warp) order
-    constexpr int NSEG = ((T / 16 + kThreads - 1) / kThreads) * kWarps;
-    const int *seg_cnt = sm.scratch + kScrCnt;
-    int n_cand = 0;
-#pragma unroll
-    for (int q = 0; q < NSEG; q++) n_cand += seg_cnt[q];
-    unsigned g_off = (unsigned)tile * kTileSlots;
-    if (n_cand > kTileSlots) {
-        // the rare tile with more candidates than its fixed block takes space from the overflow area (one more barrier)
-        if (tid == 0)
-            sm.scratch[kScrOff] = (int)((unsigned)P.n_tiles_total * kTileSlots +
-                                        (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand));
-        gb.sync();
-        g_off = (unsigned)sm.scratch[kScrOff];
-    }
-    if (tid == n_warps * 32 - 32) publish_tile<SPS>(P, sm, tile, n_cand, g_off);
-    if (n_cand == 0) return;
-    const bool fast = SPS != 0 && ((unsigned)tile - P.fast_lo) <= P.fast_span && P.fast_span != 0xffffffffu;
-    // candidate c lives in the last segment that starts at or before c (counts re-read from shared memory: a few
-    // broadcast loads per task instead of 8 registers held across the sort)
-    auto list_at = [&](int c) -> unsigned {
-        int seg = 0, before = 0, acc = 0;
-#pragma unroll
-        for (int q = 0; q < NSEG; q++) {
-            if (acc <= c) {
-                seg = q;
-                before = acc;
-            }
-            acc += seg_cnt[q];
-        }
-        return sm.list[seg * kSegCap + c - before];
-    };
-#else
     const int n_cand = sm.scratch[kScrNCand];
     if (n_cand == 0) return;
     const bool fast = sm.scratch[kScrFast] != 0;
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
-    auto list_at = [&](int c) -> unsigned { return sm.list[c]; };
-#endif
 
     // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
     // interior tiles: candidates go in pairs (half-warp each) and every pair is two tasks -- median/SNR and
@@ -1236,8 +838,8 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     for (int t = wid; t < n_tasks; t += n_warps) {
         const int c = (t >> 1) * 2;
         const bool two = c + 1 < n_cand;
-        const unsigned e0 = list_at(c);
-        const unsigned e1 = two ? list_at(c + 1) : e0;
+        const unsigned e0 = sm.list[c];
+        const unsigned e1 = two ? sm.list[c + 1] : e0;
         if (g_off + (unsigned)c + 1u >= P.cand_cap) {
             if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
             continue;
@@ -1286,13 +888,7 @@ __global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTA
     const long long tile = (long long)P.tile_first + blockIdx.x;
     const CtaBar gb;
     scan_tile<SPS, FMT>(P, sm, tile, gb);
-#if !ADSB_OPT_WARP_LISTS
     gb.sync();
-#endif
-#if ADSB_OPT_LATE_HEADER && !ADSB_OPT_COMPACT_W0 && !ADSB_OPT_WARP_LISTS
-    if (threadIdx.x == kThreads - 32)           // the last warp is the least likely to hold a slice task
-        publish_tile<SPS>(P, sm, tile, sm.scratch[kScrNCand], (unsigned)sm.scratch[kScrOff]);
-#endif
     slice_tile<SPS, FMT>(P, sm, tile, (int)threadIdx.x, kWarps, gb);
 }
 

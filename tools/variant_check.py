@@ -20,7 +20,8 @@ sys.path.insert(0, ROOT)
 CSRC = os.path.join(ROOT, "gr_adsb_b200", "csrc")
 VDIR = os.path.join(CSRC, "variants")
 
-_OPTS = ["COMPACT_W0", "MEDIAN_MID", "PREFETCH_OWN", "PREFILTER_SIGN", "LATE_HEADER", "WARP_LISTS"]
+# compile-time switches currently under test (adsb_scan.cuh / adsb_device.cuh); "default" = the source as it is
+_OPTS = []
 
 
 def _defs(*on):
@@ -28,18 +29,7 @@ def _defs(*on):
 
 
 VARIANTS = {
-    "base": _defs(),
-    "midsgn": _defs("MEDIAN_MID", "PREFILTER_SIGN"),
-    "midsgnpf": _defs("MEDIAN_MID", "PREFILTER_SIGN", "PREFETCH_OWN"),
-    "midsgnpflate": _defs("MEDIAN_MID", "PREFILTER_SIGN", "PREFETCH_OWN", "LATE_HEADER"),
-    "late": _defs("LATE_HEADER"),
-    "wl": _defs("WARP_LISTS"),
-    "midsgnpfwl": _defs("MEDIAN_MID", "PREFILTER_SIGN", "PREFETCH_OWN", "WARP_LISTS"),
-    "allsgn": _defs("COMPACT_W0", "MEDIAN_MID", "PREFETCH_OWN", "PREFILTER_SIGN"),
-    "all": _defs("COMPACT_W0", "MEDIAN_MID", "PREFETCH_OWN"),
-    "w0": _defs("COMPACT_W0"),
-    "mid": _defs("MEDIAN_MID"),
-    "sgn": _defs("PREFILTER_SIGN"),
+    "default": _defs(),
 }
 
 
