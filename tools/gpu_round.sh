@@ -9,7 +9,7 @@ T0=$(date +%s)
 el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
 el start
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv,noheader
-timeout 170 python tools/variant_check.py run --variants base,midsgn,midsgnpf,midsgnpflate,midsgnpfwl,wl,late,midsgnpf@148,midsgnpf@444 --iters 30 > gpurun_out/variants.log 2>&1
+timeout 170 python tools/variant_check.py run --variants default,cmp,ent,s19,rows,prmt,all5,all4,c3,c3r --iters 24 > gpurun_out/variants.log 2>&1
 el "variants rc=$?"
 BESTFULL=$(cat gpurun_out/best_variant.txt 2>/dev/null || echo base)
 BEST=${BESTFULL%@*}
