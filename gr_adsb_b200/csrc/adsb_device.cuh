@@ -19,9 +19,6 @@
 #define ADSB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
-#ifndef ADSB_OPT_SORT19
-#define ADSB_OPT_SORT19 0      // in-lane 8-key sort by the 19-comparator odd-even merge network (A/B switch)
-#endif
 
 namespace adsb {
 
@@ -280,7 +277,6 @@ __device__ __forceinline__ void warp_sort128(unsigned (&k)[4], int lane)
 __device__ __forceinline__ void half_mid128(unsigned (&k)[8], int lane, unsigned &lo_mid, unsigned &hi_mid, unsigned &top)
 {
     // each lane's 8 keys ascending
-#if ADSB_OPT_SORT19
     // Batcher's odd-even merge sort of 8: 19 comparators instead of the bitonic network's 24
     cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
     cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
@@ -288,17 +284,6 @@ __device__ __forceinline__ void half_mid128(unsigned (&k)[8], int lane, unsigned
     cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
     cex(k[2], k[4]); cex(k[3], k[5]);
     cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
-#else
-#pragma unroll
-    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-    cex(k[0], k[3]); cex(k[1], k[2]); cex(k[4], k[7]); cex(k[5], k[6]);
-#pragma unroll
-    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-    cex(k[0], k[7]); cex(k[1], k[6]); cex(k[2], k[5]); cex(k[3], k[4]);
-    cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
-#pragma unroll
-    for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
-#endif
 #pragma unroll
     for (int size = 16; size <= 64; size <<= 1) {
         {

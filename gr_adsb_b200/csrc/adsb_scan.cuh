@@ -17,19 +17,6 @@ namespace adsb {
 #ifndef ADSB_MIN_CTAS_BIG
 #define ADSB_MIN_CTAS_BIG 4  // same for the 8192-sample tile kernels (8 Msps and unspecialised rates)
 #endif
-// compile-time switches under A/B measurement (tools/variant_check.py)
-#ifndef ADSB_OPT_CMP_REDUX
-#define ADSB_OPT_CMP_REDUX 0   // compaction offsets from one load per lane + warp reductions / ballot ranks
-#endif
-#ifndef ADSB_OPT_P1_WARPROWS
-#define ADSB_OPT_P1_WARPROWS 0 // phase 1: a warp loads consecutive 32-sample rows (its bitmap words are stored in pairs)
-#endif
-#ifndef ADSB_OPT_BITS_PRMT
-#define ADSB_OPT_BITS_PRMT 0   // PPM slice: a half-warp's ballot halves packed by byte permutes
-#endif
-#ifndef ADSB_OPT_ENT_REG
-#define ADSB_OPT_ENT_REG 0     // a thread's single candidate keeps its centre slot in a register (no bitmap walk at compaction)
-#endif
 #ifndef ADSB_LMAX2
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
@@ -372,7 +359,6 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
         flags = kHitDemodValid;
         const float *sob = mp + 8 * SPS;                       // demod.py:75
         unsigned syn = 0;
-#if ADSB_OPT_BITS_PRMT
         unsigned bal[8];
         bal[7] = 0u;
 #pragma unroll
@@ -386,16 +372,6 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
         const unsigned sel = (lane & 16) ? 0x7632u : 0x5410u;
 #pragma unroll
         for (int q = 0; q < 4; q++) w[q] = __byte_perm(bal[2 * q], bal[2 * q + 1], sel);
-#else
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const int bi = j * 16 + hl;
-            const bool bit = sob[bi * SPS] > sob[bi * SPS + H];   // demod.py:87-95
-            const unsigned bal = __ballot_sync(kFull, bit);
-            w[j >> 1] |= ((bal >> (lane & 16)) & 0xffffu) << (16 * (j & 1));
-            syn ^= bit ? P.crc_tab[bi] : 0u;
-        }
-#endif
 #pragma unroll
         for (int d = 8; d > 0; d >>= 1) syn ^= __shfl_xor_sync(kFull, syn, d);
         const unsigned df = __brev(w[0]) >> 27;
@@ -450,24 +426,14 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     }
     if (fast) {
         constexpr int U = 6;
-#if ADSB_OPT_P1_WARPROWS
-        // slot u of warp wid covers the 32 samples from wid * NPT * 32 + u * 32: every load is still one coalesced
-        // row, and a warp's bitmap words are consecutive, so lane 0 stores them in pairs (when NPT is even)
+        // slot u of warp wid covers the 32 samples from (wid * NPT + u) * 32: every load is one coalesced row and a
+        // warp's bitmap words are consecutive, so lane 0 stores them in pairs (when NPT is even: 8-byte alignment)
         const int p1_base = wid * (G::NPT * 32) + lane;
-        constexpr int p1_step = 32;
         const int p1_word = wid * G::NPT;
-        constexpr int p1_wstep = 1;
         constexpr bool p1_pairs = (G::NPT % 2) == 0;
-#else
-        const int p1_base = tid;
-        constexpr int p1_step = kThreads;
-        const int p1_word = wid;
-        constexpr int p1_wstep = kWarps;
-        constexpr bool p1_pairs = false;
-#endif
         unsigned w_even = 0;
         auto put = [&](int u, float x) {
-            sm.mag[p1_base + u * p1_step] = x;
+            sm.mag[p1_base + u * 32] = x;
             const unsigned w = __ballot_sync(kFull, x >= thr);
             if (p1_pairs) {
                 if (u & 1) {
@@ -476,7 +442,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     w_even = w;
                 }
             } else if (lane == 0) {
-                sm.bits[p1_word + u * p1_wstep] = w;
+                sm.bits[p1_word + u] = w;
             }
         };
         if (FMT == kFmtC64) {
@@ -486,7 +452,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 unsigned long long v[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    if (u0 + u < G::NPT) v[u] = ldg_stream_b64(src + (u0 + u) * p1_step);
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_b64(src + (u0 + u) * 32);
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (u0 + u < G::NPT) put(u0 + u, mag2_packed(v[u]));
@@ -498,7 +464,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 unsigned v[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    if (u0 + u < G::NPT) v[u] = ldg_stream_b32(src + (u0 + u) * p1_step);
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_b32(src + (u0 + u) * 32);
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (u0 + u < G::NPT) put(u0 + u, mag2_sc16(v[u]));
@@ -510,7 +476,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 float v[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    if (u0 + u < G::NPT) v[u] = ldg_stream_f1(src + (u0 + u) * p1_step);
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_f1(src + (u0 + u) * 32);
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (u0 + u < G::NPT) put(u0 + u, v[u]);
@@ -534,9 +500,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     // before it in bits 0..15.  cmask: candidates keyed by the bit of their FALL inside the chunk.
     constexpr int NCH = (T / 16 + kThreads - 1) / kThreads;
     unsigned cmask[NCH], lmask[NCH];
-#if ADSB_OPT_ENT_REG
     int cent[NCH];              // centre slot of the candidate found last in this thread's chunk (valid when it has exactly one)
-#endif
     int tmax = -1;              // largest centre (shared-memory slot) of a complete short pulse
     unsigned tflags = 0;
     bool have_long = false;
@@ -545,9 +509,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         const int c = tid + ci * kThreads;
         cmask[ci] = 0;
         lmask[ci] = 0;
-#if ADSB_OPT_ENT_REG
         cent[ci] = 0;
-#endif
         if (c >= T / 16) continue;
         const int wq = kLeftHalo / 32 + (c >> 1);
         const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
@@ -589,9 +551,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 if (preamble_match<G::H>(sm.mag + kp, h)) {
                     cm |= 1u << b;
                     if (kp < kNoise) lm |= 1u << b;             // noise window leaves the staged span
-#if ADSB_OPT_ENT_REG
                     cent[ci] = kp;
-#endif
                 }
             }
             if (C) {
@@ -637,9 +597,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                         // key the candidate by its fall: first zero above the centre
                         const int fb = pc + __ffs(~(W >> (pc + 1)));
                         cm |= 1u << (fb - 16);
-#if ADSB_OPT_ENT_REG
                         cent[ci] = k0 + pc - 16;
-#endif
                     }
                 }
             }
@@ -674,9 +632,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 tmax = kp > tmax ? kp : tmax;
                 if (preamble_match<0>(sm.mag + kp, h)) {
                     cm |= 1u << b;
-#if ADSB_OPT_ENT_REG
                     cent[ci] = kp;
-#endif
                 }
             }
         }
@@ -800,23 +756,12 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         int base = 0;
 #pragma unroll
         for (int ci = 0; ci < NCH; ci++) {
-#if ADSB_OPT_CMP_REDUX
             // lane q < 8 holds warp q's count: two warp reductions give this warp's offset and the row total
             const int v = (lane < kWarps) ? s_cnt[ci][lane] : 0;
             const int before = wtot[ci] ? __reduce_add_sync(kFull, lane < wid ? v : 0) : 0;
             const int total = (ci + 1 < NCH) ? __reduce_add_sync(kFull, v) : 0;
-#else
-            int before = 0, total = 0;
-#pragma unroll
-            for (int q = 0; q < kWarps; q++) {
-                const int v = s_cnt[ci][q];
-                before += (q < wid) ? v : 0;
-                total += v;
-            }
-#endif
             if (wtot[ci]) {
                 const int cnt = __popc(cmask[ci]);
-#if ADSB_OPT_CMP_REDUX
                 // rank inside the warp: a ballot when no lane holds more than one candidate (the usual case)
                 const unsigned has = __ballot_sync(kFull, cnt != 0);
                 int excl = __popc(has & ((1u << lane) - 1u));
@@ -830,23 +775,12 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     excl = inc - cnt;
                 }
                 int off = base + before + excl;
-#else
-                int inc = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(kFull, inc, d);
-                    if (lane >= d) inc += t;
-                }
-                int off = base + before + inc - cnt;
-#endif
                 unsigned cm = cmask[ci];
                 const int k0 = kLeftHalo + (tid + ci * kThreads) * 16;
-#if ADSB_OPT_ENT_REG
                 if (cnt == 1 && lmask[ci] == 0) {
                     sm.list[off] = (unsigned short)cent[ci];        // centre kept since detection
                     cm = 0;
                 }
-#endif
                 while (cm) {
                     const int b = __ffs(cm) - 1;
                     cm &= cm - 1;

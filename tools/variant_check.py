@@ -21,7 +21,7 @@ CSRC = os.path.join(ROOT, "gr_adsb_b200", "csrc")
 VDIR = os.path.join(CSRC, "variants")
 
 # compile-time switches currently under test (adsb_scan.cuh / adsb_device.cuh); "default" = the source as it is
-_OPTS = ["CMP_REDUX", "ENT_REG", "SORT19", "P1_WARPROWS", "BITS_PRMT"]
+_OPTS = []           # e.g. ["FOO"] for a block guarded by `#if ADSB_OPT_FOO` in csrc/
 
 
 def _defs(*on):
@@ -30,15 +30,6 @@ def _defs(*on):
 
 VARIANTS = {
     "default": _defs(),
-    "cmp": _defs("CMP_REDUX"),
-    "ent": _defs("ENT_REG"),
-    "s19": _defs("SORT19"),
-    "rows": _defs("P1_WARPROWS"),
-    "prmt": _defs("BITS_PRMT"),
-    "all5": _defs("CMP_REDUX", "ENT_REG", "SORT19", "P1_WARPROWS", "BITS_PRMT"),
-    "all4": _defs("CMP_REDUX", "ENT_REG", "SORT19", "BITS_PRMT"),
-    "c3": _defs("CMP_REDUX", "SORT19", "BITS_PRMT"),
-    "c3r": _defs("CMP_REDUX", "SORT19", "BITS_PRMT", "P1_WARPROWS"),
 }
 
 
