@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--sps", type=int, default=SPS, help="samples per symbol (secondary workloads; default 2)")
     ap.add_argument("--density", type=float, default=DENSITY, help="bursts per sample (default 5e-3 = 10k/s at 2 Msps)")
     ap.add_argument("--sc16", action="store_true", help="feed interleaved int16 IQ (4 B/sample; SURVEY.md 8f-4) instead of complex64")
+    ap.add_argument("--cu8", action="store_true", help="feed interleaved uint8 IQ (2 B/sample, RTL-SDR wire format) instead of complex64")
     ap.add_argument("--fec", action="store_true", help="enable the conservative error correction (decoder.py error_corr)")
     ap.add_argument("--f32", action="store_true", help="feed float32 |IQ|^2 instead of complex64 (BASELINE configs[0] layout)")
     args = ap.parse_args()
@@ -226,7 +227,14 @@ def main():
     buf = torch.zeros((geo["n_in"], 2), dtype=torch.float32, device=dev)
     shard = buf[geo["left"]: geo["left"] + L]
     _, truth = synth.synth_torch(L, SPS, int(L * DENSITY), SEED + rank, dev, out=shard, return_truth=False)
-    is_c64 = 0 if args.f32 else (2 if args.sc16 else 1)
+    is_c64 = 0 if args.f32 else (2 if args.sc16 else (3 if args.cu8 else 1))
+    item_bytes = {0: 4, 1: 8, 2: 4, 3: 2}[is_c64]
+    fmt_name = ("float32 |IQ|^2", "complex64 IQ", "int16 IQ", "uint8 IQ")[is_c64]
+    if args.cu8:
+        work_buf = torch.clamp(torch.round(buf * 128.0 + 127.5), 0, 255).to(torch.uint8).contiguous()
+        shard = None
+        del buf
+        buf = work_buf
     if args.sc16:
         work_buf = torch.clamp(torch.round(buf * 32768.0), -32768, 32767).to(torch.int16).contiguous()
         shard = None
@@ -316,10 +324,10 @@ def main():
     ctx.profile_enable(False)
     scan_avg = float(np.mean(scan_ms))
     peak, peak_src = measured_peak()
-    alg_bytes = (8.0 if is_c64 == 1 else 4.0) * geo["n_out"]   # 8 B per complex64 (4 B per float32) sample, read once
+    alg_bytes = float(item_bytes) * geo["n_out"]   # 8 B per complex64 (4 B float32 / int16 IQ, 2 B uint8 IQ) sample, read once
     achieved = alg_bytes / (scan_avg * 1e-3) / 1e9
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "scan_slice_kernel<sps=%d,%s>" % (SPS, ("float32", "complex64", "sc16")[is_c64]), "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "scan_slice_kernel<sps=%d,%s>" % (SPS, ("float32", "complex64", "sc16", "cu8")[is_c64]), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_avg,
@@ -332,9 +340,9 @@ def main():
             "hits_per_step": n_hits, "candidates_per_step": n_cand, "crc_pass_per_step": n_crc,
             "crc_pass_bursts_per_s": n_crc / (ms_per_step * 1e-3),
             "roofline": roofline}
-    if args.sps != 2 or args.density != 5e-3 or args.f32 or args.fec or args.sc16:
+    if args.sps != 2 or args.density != 5e-3 or args.f32 or args.fec or args.sc16 or args.cu8:
         line["config"]["workload"] = ("secondary workload (not the headline): %d Msps %s, %.3g bursts/sample, threshold %.3g, "
-                                      "whole-buffer semantics" % (SPS, "float32 |IQ|^2" if args.f32 else ("int16 IQ" if args.sc16 else "complex64 IQ"), DENSITY, THRESHOLD))
+                                      "whole-buffer semantics" % (SPS, fmt_name, DENSITY, THRESHOLD))
     if args.fec:
         line["error_correction"] = {"mode": "Conservative (decoder.py:738-763)", "fixed_per_step_rank0": counters["n_fec_fixed"]}
     if world > 1:
@@ -342,7 +350,7 @@ def main():
                          "unsettled_steps": counters["carry_unstable"]}
 
     # ---- end to end through the C ABI with HOST buffers (H2D of the samples + D2H of the hits timed)
-    if rank == 0 and not args.no_e2e and is_c64 in (1, 2):
+    if rank == 0 and not args.no_e2e and is_c64 in (1, 2, 3):
         try:
             src = buf[geo["left"]: geo["left"] + L]
             host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
@@ -356,12 +364,11 @@ def main():
                 ctx.reset_state()
                 n_e2e = ctx.burst_work_ptr(host.data_ptr(), is_c64, L, L, 8 * SPS - 1, THRESHOLD, 0, hits)
             dt = (time.perf_counter() - t0) / args.e2e_steps
-            item = 8 if is_c64 == 1 else 4
-            line["e2e"] = {"value": L / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": L * item,
+            line["e2e"] = {"value": L / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": L * item_bytes,
                            "d2h_bytes_per_step": int(n_e2e) * 32 + 96, "steps": args.e2e_steps,
                            "ms_per_step": dt * 1e3, "hits_per_step": int(n_e2e),
                            "api": "adsb_burst_work (pinned host %s in, adsb_hit[] out), 1 GPU"
-                                  % ("complex64" if is_c64 == 1 else "int16 IQ")}
+                                  % fmt_name}
             del host
         except Exception as e:           # pragma: no cover
             line["e2e"] = {"error": repr(e)}

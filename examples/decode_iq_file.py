@@ -4,7 +4,8 @@
     python examples/decode_iq_file.py capture.fc32 --fs 2e6 --threshold 0.01 [--fec] [--max 20]
 
 The file holds interleaved float32 I/Q (GNU Radio file_sink of a complex stream; what
-examples/adsb_rx.py's USRP source produces).  For every burst whose parity checks out it prints the
+examples/adsb_rx.py's USRP source produces); `--format sc16` / `--format cu8` read interleaved int16 / uint8 I/Q
+instead (USRP wire format / rtl_sdr output), widened on the device.  For every burst whose parity checks out it prints the
 sample offset, SNR and the 112-bit message as hex -- the input the reference adsb.decoder works on.
 `--synth N` writes a synthetic N-sample capture first (handy where no recording is at hand).
 """
@@ -26,13 +27,23 @@ def main():
     ap.add_argument("--threshold", type=float, default=0.01)
     ap.add_argument("--fec", action="store_true", help='decoder error_corr="Conservative" on the GPU')
     ap.add_argument("--max", type=int, default=20, help="messages to print")
+    ap.add_argument("--format", default="fc32", choices=["fc32", "sc16", "cu8"], help="sample format of the file")
     ap.add_argument("--synth", type=int, default=0, help="first write a synthetic capture of this many samples")
     a = ap.parse_args()
     sps = int(a.fs // 1e6)
     if a.synth:
         d = synth.synth_numpy(a.synth, sps=sps, n_bursts=max(1, a.synth // 2000), seed=1, nonoverlap=True)
-        d["iq"].tofile(a.path)
-    iq = np.fromfile(a.path, dtype=np.complex64)
+        ri = d["iq"].view(np.float32).reshape(-1, 2)
+        if a.format == "sc16":
+            np.clip(np.round(ri * 32768.0), -32768, 32767).astype(np.int16).tofile(a.path)
+        elif a.format == "cu8":
+            np.clip(np.round(ri * 128.0 + 127.5), 0, 255).astype(np.uint8).tofile(a.path)
+        else:
+            d["iq"].tofile(a.path)
+    if a.format == "fc32":
+        iq = np.fromfile(a.path, dtype=np.complex64)
+    else:
+        iq = np.fromfile(a.path, dtype=np.int16 if a.format == "sc16" else np.uint8).reshape(-1, 2)
     ctx = g.Context(sps, len(iq))
     if a.fec:
         ctx.set_error_correction(g.FEC_CONSERVATIVE)

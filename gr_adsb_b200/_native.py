@@ -21,7 +21,7 @@ HIT_CRC_OK = 0x2
 HIT_LATE_TAG = 0x4
 HIT_FEC_FIXED = 0x8
 FEC_NONE, FEC_CONSERVATIVE = 0, 1
-FMT_F32, FMT_C64, FMT_SC16 = 0, 1, 2
+FMT_F32, FMT_C64, FMT_SC16, FMT_CU8 = 0, 1, 2, 3
 CARRY_USED_ON_DEVICE = -(1 << 63)
 
 HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
@@ -210,7 +210,8 @@ class Context(object):
         return bits, valid
 
     def burst_work(self, buf, n_out=None, lead=None, threshold=0.01, base=0, cap=None):
-        """Fused path over a host buffer (float32 |IQ|^2, complex64 IQ or int16[n,2] sc16 IQ) -> structured hits."""
+        """Fused path over a host buffer (float32 |IQ|^2, complex64 IQ, int16[n,2] sc16 IQ or uint8[n,2] cu8 IQ)
+        -> structured hits."""
         buf = np.ascontiguousarray(buf)
         if buf.dtype == np.complex64:
             c64 = FMT_C64
@@ -218,8 +219,10 @@ class Context(object):
             c64 = FMT_F32
         elif buf.dtype == np.int16 and buf.ndim == 2 and buf.shape[1] == 2:
             c64 = FMT_SC16                       # interleaved int16 I/Q, value = int * 2**-15
+        elif buf.dtype == np.uint8 and buf.ndim == 2 and buf.shape[1] == 2:
+            c64 = FMT_CU8                        # interleaved uint8 I/Q, value = (u - 127.5) / 128 (RTL-SDR)
         else:
-            raise TypeError("burst_work takes float32 |IQ|^2, complex64 IQ or int16[n,2] IQ")
+            raise TypeError("burst_work takes float32 |IQ|^2, complex64 IQ, int16[n,2] IQ or uint8[n,2] IQ")
         n_in = len(buf)
         if lead is None:
             lead = self.hist if n_out is None else int(n_out) + self.hist - n_in

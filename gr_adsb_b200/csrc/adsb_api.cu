@@ -102,7 +102,7 @@ struct adsb_ctx {
     size_t d_mag_cap;
     int staged_fmt;              // format / item count of the input adsb_burst_work staged last (-1: none)
     size_t staged_n;
-    bool scan_configured[3];     // per sample format: shared-memory attributes of the scan kernel set on this device
+    bool scan_configured[kNumFmt];  // per sample format: shared-memory attributes of the scan kernel set on this device
     Rec *h_tmp;                  // host scratch of the two-block entry points
     size_t h_tmp_cap;
     unsigned char *h_bits;
@@ -231,6 +231,7 @@ cudaError_t launch_scan_f(const ScanParams &P, int fmt, unsigned n_blocks, cudaS
     switch (fmt) {
     case kFmtC64: return launch_scan_t<SPS, kFmtC64>(P, n_blocks, s, configured);
     case kFmtSC16: return launch_scan_t<SPS, kFmtSC16>(P, n_blocks, s, configured);
+    case kFmtCU8: return launch_scan_t<SPS, kFmtCU8>(P, n_blocks, s, configured);
     default: return launch_scan_t<SPS, kFmtF32>(P, n_blocks, s, configured);
     }
 }
@@ -633,7 +634,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
                         size_t halo_left, float threshold, int64_t base, int64_t eob_in, void *stream,
                         const adsb_hit **d_hits)
 {
-    if (!ctx || !d_in || is_c64 < 0 || is_c64 > 2) return ADSB_E_INVAL;
+    if (!ctx || !d_in || is_c64 < 0 || is_c64 >= kNumFmt) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, halo_left, true);
     if (rc) return rc;
     ON_DEVICE(ctx);
@@ -751,11 +752,11 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
 int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size_t lead, size_t n_out,
                     float threshold, int64_t base, adsb_hit *hits, size_t cap, size_t *n_hits)
 {
-    if (!ctx || !in || is_c64 < 0 || is_c64 > 2) return ADSB_E_INVAL;
+    if (!ctx || !in || is_c64 < 0 || is_c64 >= kNumFmt) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, 0);
     if (rc) return rc;
     ON_DEVICE(ctx);
-    const size_t isz = (is_c64 == kFmtC64) ? 8 : 4;
+    const size_t isz = (is_c64 == kFmtC64) ? 8 : (is_c64 == kFmtCU8) ? 2 : 4;
     ctx->staged_fmt = -1;
     if ((rc = ensure_input(ctx, n_in * isz))) return rc;
     const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
@@ -823,6 +824,7 @@ int adsb_burst_mag_out(adsb_ctx *ctx, float *out, size_t n_out)
     switch (ctx->staged_fmt) {
     case kFmtC64: ADSB_LAUNCH(mag_out_kernel<kFmtC64>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
     case kFmtSC16: ADSB_LAUNCH(mag_out_kernel<kFmtSC16>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
+    case kFmtCU8: ADSB_LAUNCH(mag_out_kernel<kFmtCU8>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
     default: ADSB_LAUNCH(mag_out_kernel<kFmtF32>, blocks, kThreads, 0, s, ctx->d_in, first, (long long)n_out, ctx->d_mag); break;
     }
     CK(cudaGetLastError());

@@ -66,7 +66,7 @@ struct Header {
 };
 
 struct ScanParams {
-    const void *in;        // float (|IQ|^2), float2 (IQ) or short2 (sc16 IQ)
+    const void *in;        // float (|IQ|^2), float2 (IQ), short2 (sc16 IQ) or uchar2 (cu8 IQ)
     long long n_arr;       // items in `in`
     long long lead;        // virtual zero items before in[0]; window index = array index + lead
     long long n_loc;       // lead + n_arr
@@ -153,7 +153,15 @@ __device__ __forceinline__ float mag2(float2 v)
 // input sample formats of the scan kernel
 enum { kFmtF32 = 0,     // float32 |IQ|^2 (what framer.work() is handed)
        kFmtC64 = 1,     // complex64 IQ (the USRP source's fc32 stream)
-       kFmtSC16 = 2 };  // interleaved int16 IQ, value = int * 2^-15 (the wire format of most SDRs)
+       kFmtSC16 = 2,    // interleaved int16 IQ, value = int * 2^-15 (the wire format of most SDRs)
+       kFmtCU8 = 3 };   // interleaved uint8 IQ, value = (u - 127.5) / 128 (RTL-SDR dongles, the usual 1090 MHz receiver)
+constexpr int kNumFmt = 4;
+
+template <int FMT>
+__host__ __device__ constexpr int item_bytes()
+{
+    return FMT == kFmtC64 ? 8 : FMT == kFmtCU8 ? 2 : 4;
+}
 
 // |IQ|^2 of one sc16 sample (re in the low half): widen, scale by 2^-15 (exact), then as mag2()
 __device__ __forceinline__ float mag2_sc16(unsigned v)
@@ -161,6 +169,25 @@ __device__ __forceinline__ float mag2_sc16(unsigned v)
     const float re = __fmul_rn(__int2float_rn((int)(short)(v & 0xffffu)), 3.0517578125e-05f);
     const float im = __fmul_rn(__int2float_rn((int)(short)(v >> 16)), 3.0517578125e-05f);
     return __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+}
+
+// |IQ|^2 of one cu8 sample (re in the low byte): (u - 127.5) / 128 is exact in float32, then as mag2()
+__device__ __forceinline__ float mag2_cu8(unsigned v)
+{
+    const float re = __fmul_rn(__fadd_rn(__int2float_rn((int)(v & 0xffu)), -127.5f), 0.0078125f);
+    const float im = __fmul_rn(__fadd_rn(__int2float_rn((int)((v >> 8) & 0xffu)), -127.5f), 0.0078125f);
+    return __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+}
+
+__device__ __forceinline__ unsigned ldg_stream_b16(const void *p)
+{
+    unsigned short v;
+#if defined(ADSB_HOST_EMU)
+    memcpy(&v, p, 2);
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.b16 %0, [%1];" : "=h"(v) : "l"(p));
+#endif
+    return v;
 }
 
 __device__ __forceinline__ unsigned ldg_stream_b32(const void *p)
@@ -179,6 +206,7 @@ __device__ __forceinline__ float load_x(const void *in, long long j)
 {
     if (FMT == kFmtC64) return mag2(ldg_stream_f2(reinterpret_cast<const float2 *>(in) + j));
     if (FMT == kFmtSC16) return mag2_sc16(ldg_stream_b32(reinterpret_cast<const unsigned *>(in) + j));
+    if (FMT == kFmtCU8) return mag2_cu8(ldg_stream_b16(reinterpret_cast<const unsigned short *>(in) + j));
     return ldg_stream_f1(reinterpret_cast<const float *>(in) + j);
 }
 

@@ -412,8 +412,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         if (((unsigned)ta - P.fast_lo) <= P.fast_span) {
             // only that tile's own T samples: its halos are the neighbouring tiles' own ranges, prefetched by the
             // CTAs that run next to this one; T * itemsize / 128 lines = one per thread for complex64 at T = 4096
-            const char *base = reinterpret_cast<const char *>(P.in) + ta * T * (FMT == kFmtC64 ? 8 : 4);
-            constexpr int kLines = T * (FMT == kFmtC64 ? 8 : 4) / 128;
+            const char *base = reinterpret_cast<const char *>(P.in) + ta * T * item_bytes<FMT>();
+            constexpr int kLines = T * item_bytes<FMT>() / 128;
 #if !defined(ADSB_HOST_EMU)
 #pragma unroll
             for (int l = tid; l < kLines; l += kThreads)
@@ -468,6 +468,18 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (u0 + u < G::NPT) put(u0 + u, mag2_sc16(v[u]));
+            }
+        } else if (FMT == kFmtCU8) {
+            const unsigned short *src = reinterpret_cast<const unsigned short *>(P.in) + (a0 - kLeftHalo) + p1_base;
+#pragma unroll
+            for (int u0 = 0; u0 < G::NPT; u0 += U) {
+                unsigned v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (u0 + u < G::NPT) v[u] = ldg_stream_b16(src + (u0 + u) * 32);
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (u0 + u < G::NPT) put(u0 + u, mag2_cu8(v[u]));
             }
         } else {
             const float *src = reinterpret_cast<const float *>(P.in) + (a0 - kLeftHalo) + p1_base;

@@ -35,6 +35,7 @@ extern "C" {
 #define ADSB_FMT_F32 0
 #define ADSB_FMT_C64 1
 #define ADSB_FMT_SC16 2
+#define ADSB_FMT_CU8 3
 
 enum {
     ADSB_OK = 0,
@@ -122,7 +123,8 @@ int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *so
 /* Fused path over a HOST buffer: |IQ|^2 where needed, framer, demod and parity check in one pass on the
  * GPU.  `is_c64` selects the item format: ADSB_FMT_F32 (0) float32 |IQ|^2, ADSB_FMT_C64 (1) interleaved re,im
  * float32 pairs, ADSB_FMT_SC16 (2) interleaved re,im int16 with value = int * 2^-15 (UHD sc16 wire format /
- * blocks.interleaved_short_to_complex with scale 32768); n_in counts items (complex samples).  The window is `lead` zero items followed by in[0:n_in]; n_out + 8*sps - 1 == lead + n_in.
+ * blocks.interleaved_short_to_complex with scale 32768), ADSB_FMT_CU8 (3) interleaved re,im uint8 with value =
+ * (u - 127.5) / 128 (RTL-SDR wire format); n_in counts items (complex samples).  The window is `lead` zero items followed by in[0:n_in]; n_out + 8*sps - 1 == lead + n_in.
  * lead = 8*sps-1 with a freshly reset context reproduces a flowgraph's first work() call over
  * the whole buffer ("whole-buffer mode"); lead = 0 continues a stream whose history the caller
  * prepends, exactly like adsb_framer_work.  hits[i].idx = base + window index. */

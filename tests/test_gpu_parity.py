@@ -322,3 +322,4 @@ def test_sc16_input_matches_oracle(sps, seed):
     crc = np.array([co.crc_pass(b) for b in ref["pdu_bits"]], np.uint8)
     check_fused(hits, sps, ref["tag_off"], ref["tag_snr"], ref["pdu_off"], ref["pdu_bits"], crc)
     assert len(hits) > 20
+
