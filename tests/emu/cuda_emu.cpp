@@ -14,6 +14,7 @@
 #include <ucontext.h>
 #endif
 
+#include <map>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -26,7 +27,7 @@ dim3 g_blockDim, g_gridDim;
 namespace {
 
 constexpr size_t kStackBytes = 256 * 1024;
-unsigned char g_smem[232448] __attribute__((aligned(128)));     // the block's dynamic shared memory
+unsigned char g_smem[232448 + 256] __attribute__((aligned(128)));     // the block's dynamic shared memory + canary
 
 struct Warp {
     int expected, arrived;
@@ -166,6 +167,51 @@ unsigned next_random()
 
 }  // namespace
 
+// ---- guarded "device" memory -----------------------------------------------------------------------------------
+namespace {
+constexpr size_t kGuard = 256;                 // bytes of canary on each side of an allocation
+constexpr unsigned char kCanary = 0xC7;
+std::map<void *, size_t> g_allocs;             // user pointer -> size
+
+void check_guards(const char *when)
+{
+    for (const auto &a : g_allocs) {
+        const unsigned char *u = static_cast<const unsigned char *>(a.first);
+        for (size_t i = 0; i < kGuard; i++)
+            if (u[-(long)kGuard + (long)i] != kCanary || u[a.second + i] != kCanary) {
+                fprintf(stderr, "cuda_emu: write outside a %zu-byte device buffer (%s the buffer), found %s\n", a.second,
+                        u[a.second + i] != kCanary ? "after" : "before", when);
+                abort();
+            }
+    }
+}
+}  // namespace
+
+void *guarded_alloc(size_t n)
+{
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 256, n + 2 * kGuard)) return nullptr;
+    unsigned char *u = static_cast<unsigned char *>(raw);
+    memset(u, kCanary, kGuard);
+    memset(u + kGuard, 0xA5, n);               // fresh device memory is not zero
+    memset(u + kGuard + n, kCanary, kGuard);
+    g_allocs[u + kGuard] = n;
+    return u + kGuard;
+}
+
+void guarded_free(void *p)
+{
+    if (!p) return;
+    check_guards("at cudaFree");
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) {
+        fprintf(stderr, "cuda_emu: cudaFree of a pointer cudaMalloc did not return\n");
+        abort();
+    }
+    g_allocs.erase(it);
+    free(static_cast<unsigned char *>(p) - kGuard);
+}
+
 int lane_id() { return g_cur->lane; }
 unsigned char *dynamic_smem() { return g_smem; }
 
@@ -222,7 +268,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     if (g_cur) die("nested kernel launch");
     const unsigned n_threads = block.x * block.y * block.z;
     if (n_threads == 0 || n_threads > 1024) die("bad block size");
-    if (smem_bytes > sizeof(g_smem)) die("dynamic shared memory exceeds the emulated limit");
+    if (smem_bytes + 256 > sizeof(g_smem)) die("dynamic shared memory exceeds the emulated limit");
     static long seed = -1;
     if (seed < 0) {
         const char *e = getenv("EMU_SEED");
@@ -250,6 +296,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
                 g_blockIdx.y = by;
                 g_blockIdx.z = bz;
                 memset(g_smem, 0xA5, smem_bytes);      // uninitialised shared memory is not zero
+                memset(g_smem + smem_bytes, kCanary, kGuard);
                 for (unsigned w = 0; w < n_warps; w++) {
                     Warp &W = g_warps[w];
                     memset(&W, 0, sizeof(W));
@@ -301,8 +348,11 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
                     if (!progressed) die("deadlock: live threads wait at a collective / barrier the others never reach");
                 }
                 g_cur = nullptr;
+                for (size_t i = 0; i < kGuard; i++)
+                    if (g_smem[smem_bytes + i] != kCanary) die("write beyond the block's dynamic shared memory");
             }
     g_body = nullptr;
+    check_guards("after a kernel");
 }
 
 }  // namespace cuda_emu

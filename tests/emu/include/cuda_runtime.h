@@ -76,18 +76,20 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
     p->major = 10; p->minor = 0; p->multiProcessorCount = 1;
     return cudaSuccess;
 }
+// "device" allocations carry guard bands that cuda_emu.cpp checks after every kernel launch and at cudaFree:
+// a kernel writing outside a buffer aborts the test with the buffer's size (a memcheck for out-of-bounds writes)
+namespace cuda_emu {
+void *guarded_alloc(size_t n);
+void guarded_free(void *p);
+}
 static inline cudaError_t cudaMalloc(void **p, size_t n)
 {
-    // poison fresh "device" memory: reads of something the kernels never wrote must not look like zeros
-    void *q = nullptr;
-    if (posix_memalign(&q, 256, n ? n : 1)) return cudaErrorMemoryAllocation;
-    memset(q, 0xA5, n);
-    *p = q;
-    return cudaSuccess;
+    *p = cuda_emu::guarded_alloc(n);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void *p) { cuda_emu::guarded_free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void *p) { cuda_emu::guarded_free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
