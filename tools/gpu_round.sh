@@ -1,6 +1,8 @@
 #!/bin/bash
-# One gpurun call on a nearly spent GPU budget: A/B the scan-kernel variants, then bench / parity tests / ncu
-# with the fastest parity-green one.  Everything lands in gpurun_out/.
+# One gpurun call that does a whole measure-and-verify cycle (about 2 minutes on the box): A/B the scan-kernel
+# variants built by `python tools/variant_check.py build` (parity against the oracle and the golden vectors +
+# headline timing per variant), then bench.py, the gpu test suite, the ncu launch list and one ncu full capture
+# with the fastest parity-green one.  Everything lands in gpurun_out/.   VARIANTS=a,b,c bash tools/gpu_round.sh
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -9,7 +11,7 @@ T0=$(date +%s)
 el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
 el start
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv,noheader
-timeout 170 python tools/variant_check.py run --variants default,cmp,ent,s19,rows,prmt,all5,all4,c3,c3r --iters 24 > gpurun_out/variants.log 2>&1
+timeout 170 python tools/variant_check.py run --variants ${VARIANTS:-default} --iters 24 > gpurun_out/variants.log 2>&1
 el "variants rc=$?"
 BESTFULL=$(cat gpurun_out/best_variant.txt 2>/dev/null || echo base)
 BEST=${BESTFULL%@*}
