@@ -63,6 +63,7 @@ struct HostStage {
 
 struct adsb_ctx {
     int device, sps, T, rh, hist;
+    int nt;                      // threads per CTA of the scan kernel
     size_t max_items;
     float prev_in0;
     long long prev_eob;
@@ -207,33 +208,56 @@ void crc_table(unsigned *t)
     }
 }
 
-// `configured` = this context (one device, one sps) has already raised the kernel's shared-memory limits
-template <int SPS, int FMT>
+// `configured` = this context (one device, one sps, one CTA size) has already raised the kernel's shared-memory limits
+template <int SPS, int FMT, int NT>
 cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s, bool *configured)
 {
-    const size_t smem = tile_smem_bytes(Geo<SPS>::T, P.rh);
+    const size_t smem = tile_smem_bytes(Geo<SPS, NT>::T, P.rh, NT / 32);
     if (!*configured) {
-        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT>,
+        cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT, NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT, NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         *configured = true;
     }
-    ADSB_LAUNCH((scan_slice_kernel<SPS, FMT>), n_blocks, kThreads, smem, s, P);
+    ADSB_LAUNCH((scan_slice_kernel<SPS, FMT, NT>), n_blocks, NT, smem, s, P);
     return cudaGetLastError();
 }
 
-template <int SPS>
+template <int SPS, int NT>
 cudaError_t launch_scan_f(const ScanParams &P, int fmt, unsigned n_blocks, cudaStream_t s, bool *configured)
 {
     switch (fmt) {
-    case kFmtC64: return launch_scan_t<SPS, kFmtC64>(P, n_blocks, s, configured);
-    case kFmtSC16: return launch_scan_t<SPS, kFmtSC16>(P, n_blocks, s, configured);
-    case kFmtCU8: return launch_scan_t<SPS, kFmtCU8>(P, n_blocks, s, configured);
-    default: return launch_scan_t<SPS, kFmtF32>(P, n_blocks, s, configured);
+    case kFmtC64: return launch_scan_t<SPS, kFmtC64, NT>(P, n_blocks, s, configured);
+    case kFmtSC16: return launch_scan_t<SPS, kFmtSC16, NT>(P, n_blocks, s, configured);
+    case kFmtCU8: return launch_scan_t<SPS, kFmtCU8, NT>(P, n_blocks, s, configured);
+    default: return launch_scan_t<SPS, kFmtF32, NT>(P, n_blocks, s, configured);
     }
+}
+
+template <int NT>
+cudaError_t launch_scan_s(int sps, const ScanParams &P, int fmt, unsigned n_blocks, cudaStream_t s, bool *configured)
+{
+    switch (sps) {
+    case 2: return launch_scan_f<2, NT>(P, fmt, n_blocks, s, configured);
+    case 4: return launch_scan_f<4, NT>(P, fmt, n_blocks, s, configured);
+    case 8: return launch_scan_f<8, NT>(P, fmt, n_blocks, s, configured);
+    default: return launch_scan_f<0, NT>(P, fmt, n_blocks, s, configured);
+    }
+}
+
+// threads per CTA of the scan kernel: 256; A/B builds (-DADSB_SCAN_NT_VARIANTS) also carry 128 and 512, picked per
+// context with ADSB_SCAN_THREADS
+int scan_threads_from_env()
+{
+#ifdef ADSB_SCAN_NT_VARIANTS
+    const char *e = getenv("ADSB_SCAN_THREADS");
+    const int nt = e ? atoi(e) : kThreads;
+    if (nt == 128 || nt == 512) return nt;
+#endif
+    return kThreads;
 }
 
 cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
@@ -243,11 +267,12 @@ cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned til
     P.tile_first = tile_first;
     P.n_tiles_launch = n_blocks;
     bool *configured = &c->scan_configured[fmt];
-    switch (c->sps) {
-    case 2: return launch_scan_f<2>(P, fmt, n_blocks, s, configured);
-    case 4: return launch_scan_f<4>(P, fmt, n_blocks, s, configured);
-    case 8: return launch_scan_f<8>(P, fmt, n_blocks, s, configured);
-    default: return launch_scan_f<0>(P, fmt, n_blocks, s, configured);
+    switch (c->nt) {
+#ifdef ADSB_SCAN_NT_VARIANTS
+    case 128: return launch_scan_s<128>(c->sps, P, fmt, n_blocks, s, configured);
+    case 512: return launch_scan_s<512>(c->sps, P, fmt, n_blocks, s, configured);
+#endif
+    default: return launch_scan_s<kThreads>(c->sps, P, fmt, n_blocks, s, configured);
     }
 }
 
@@ -496,8 +521,9 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->device = device;
     ctx->sps = sps;
     ctx->hist = 8 * sps - 1;
-    ctx->T = tile_items(sps);
-    ctx->rh = right_halo(sps);
+    ctx->nt = scan_threads_from_env();
+    ctx->T = tile_items(sps, ctx->nt);
+    ctx->rh = right_halo(sps, ctx->nt);
     ctx->max_items = max_items;
     ctx->prev_in0 = 0.0f;
     ctx->prev_eob = -1;
@@ -527,7 +553,7 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     // candidates: at most one per 2 samples in theory, ~1 per 600 on busy air; size for 1 per 16.
     size_t cap = max_items / 16 + 4096;
     {
-        const size_t blocks = (max_items / (size_t)tile_items(sps) + 4) * (size_t)kTileSlots;   // fixed per-tile blocks
+        const size_t blocks = (max_items / (size_t)ctx->T + 4) * (size_t)kTileSlots;   // fixed per-tile blocks
         if (cap < 2 * blocks) cap = 2 * blocks;
     }
     if (cap > 0x7fffff00u) cap = 0x7fffff00u;

@@ -21,25 +21,28 @@ namespace adsb {
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
 
-// ---- compile-time geometry per samples-per-symbol ------------------------------------------------------
-template <int SPS>
+// ---- compile-time geometry per samples-per-symbol and CTA size -------------------------------------------
+// NT = threads per CTA (256 in the shipped build; 128 / 512 exist for A/B builds, ADSB_SCAN_NT_VARIANTS).  A thread
+// owns one 16-sample chunk of the tile (two at 8 Msps and unspecialised rates), so the tile grows with the CTA.
+template <int SPS, int NT = kThreads>
 struct Geo {
-    static constexpr int T = (SPS == 2 || SPS == 4) ? 4096 : 8192;
+    static constexpr int T = ((SPS == 2 || SPS == 4) ? 16 : 32) * NT;
     static constexpr int H = SPS / 2;                                  // 0: run-time
-    // right halo: >= 120*SPS and such that the staged span is a multiple of kThreads
-    static constexpr int RH = SPS == 2 ? 384 : SPS == 4 ? 640 : SPS == 8 ? 1152 : 0;
+    // right halo: >= 120*SPS and such that the staged span is a multiple of NT (384 / 640 / 1152 for NT = 256)
+    static constexpr int RH = SPS == 0 ? 0 : ((120 * SPS + kLeftHalo + NT - 1) / NT) * NT - kLeftHalo;
     static constexpr int S = kLeftHalo + T + RH;
-    static constexpr int NPT = S / kThreads;                           // slots per thread in phase 1
+    static constexpr int NPT = S / NT;                                 // slots per thread in phase 1
     static constexpr int LMAX = ADSB_LMAX2 > 0 && SPS == 2 ? ADSB_LMAX2 : 8;   // run lengths resolved bit-parallel
     static constexpr int DB = LMAX / 2;                                // how far a centre lies before its chunk
     static constexpr int NV = (14 + 5 * H + 4 + 1 + 3) / 4;            // float4 loads of the dense pre-filter
-    static_assert(SPS == 0 || (S % kThreads == 0 && RH >= 120 * SPS), "tile geometry");
+    static_assert(SPS == 0 || (S % NT == 0 && RH >= 120 * SPS && RH % 32 == 0), "tile geometry");
 };
 
-__host__ __device__ inline int tile_items(int sps) { return (sps == 2 || sps == 4) ? 4096 : 8192; }
-__host__ __device__ inline int right_halo(int sps)
+__host__ __device__ inline int tile_items(int sps, int nt = kThreads) { return ((sps == 2 || sps == 4) ? 16 : 32) * nt; }
+__host__ __device__ inline int right_halo(int sps, int nt = kThreads)
 {
-    return sps == 2 ? 384 : sps == 4 ? 640 : sps == 8 ? 1152 : ((120 * sps + 31) / 32) * 32;
+    if (sps == 2 || sps == 4 || sps == 8) return ((120 * sps + kLeftHalo + nt - 1) / nt) * nt - kLeftHalo;
+    return ((120 * sps + 31) / 32) * 32;
 }
 
 #ifndef ADSB_MIN_CTAS
@@ -56,12 +59,14 @@ struct TileSmem {
     unsigned short *xmask;  // T/16   extra candidate bits (by fall position) from the long-run pass
     unsigned short *xlong;  // T/16   which of them are long-run entries
     unsigned short *slow;   // kSlowCap fall slots
-    int *scratch;           // 64 ints: slots below + per-warp reduction cells
+    int *scratch;           // scratch_ints(NW): slots below + per-warp reduction cells
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
-__host__ __device__ inline size_t tile_smem_bytes(int T, int rh)
+__host__ __device__ constexpr int scratch_ints(int nw) { return 32 + 4 * nw; }      // 64 for the 8-warp CTA
+
+__host__ __device__ inline size_t tile_smem_bytes(int T, int rh, int nw = kWarps)
 {
     size_t S = (size_t)kLeftHalo + T + rh;
     size_t b = S * 4;
@@ -69,7 +74,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int T, int rh)
     b += align16(((size_t)T / 2 + 2) * 2);
     b += align16((size_t)(T / 16) * 2) * 2;
     b += align16((size_t)kSlowCap * 2);
-    b += 64 * 4;
+    b += (size_t)scratch_ints(nw) * 4;
     return b;
 }
 
@@ -94,8 +99,11 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
 }
 
 // scratch slots
-enum { kScrFast = 11, kScrTile = 12, kScrOff = 13, kScrSlowN = 14, kScrNCand = 15,
-       kScrCnt = 16 /* [2][8] */, kScrMax = 32 /* [8] */, kScrFlag = 40 /* [8] */, kScrMaxLong = 48 /* long long */ };
+enum { kScrFast = 11, kScrTile = 12, kScrOff = 13, kScrSlowN = 14, kScrNCand = 15, kScrCnt = 16 /* [2][NW] */ };
+// per-warp cells behind the counts, NW = warps per CTA: [NW] last pulse, [NW] edge flags, one long long
+__host__ __device__ constexpr int scr_max(int nw) { return kScrCnt + 2 * nw; }
+__host__ __device__ constexpr int scr_flag(int nw) { return kScrCnt + 3 * nw; }
+__host__ __device__ constexpr int scr_max_long(int nw) { return kScrCnt + 4 * nw; }
 
 // ---- thread-group barrier: scan_tile / slice_tile are written against this interface so that the phases can
 // be moved to warp groups with named barriers; a persistent 8+4-warp producer/consumer variant was measured in
@@ -385,10 +393,11 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
 
 // ---- phases 1 + 2 of one tile, by the 256 scan threads (threads 0..255 of the CTA) --------------------------
 // On return (after the caller's next group barrier) sm.list, scratch[kScrNCand|kScrOff|kScrFast] are valid.
-template <int SPS, int FMT, class GB>
+template <int SPS, int FMT, int NT, class GB>
 __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const GB gb)
 {
-    using G = Geo<SPS>;
+    using G = Geo<SPS, NT>;
+    constexpr int NW = NT / 32;                    // warps per CTA
     constexpr int T = G::T;
     const int rh = SPS ? G::RH : P.rh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;      // scan threads are threads 0..255
@@ -416,7 +425,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             constexpr int kLines = T * item_bytes<FMT>() / 128;
 #if !defined(ADSB_HOST_EMU)
 #pragma unroll
-            for (int l = tid; l < kLines; l += kThreads)
+            for (int l = tid; l < kLines; l += NT)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
 #else
             (void)base;
@@ -495,7 +504,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             }
         }
     } else {
-        for (int k = wid * 32; k < S; k += kThreads) {
+        for (int k = wid * 32; k < S; k += NT) {
             const long long i = w0 + k + lane;
             const float v = (i >= 0 && i < P.n_loc) ? window_x<FMT>(P, i) : 0.0f;
             bool bit = v >= thr;
@@ -510,7 +519,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     // ---- phase 2: falls -> pulse centres -> preamble match ----
     // Each thread owns the falls of 16-sample chunks; W holds the chunk in bits 16..31 and the 16 samples
     // before it in bits 0..15.  cmask: candidates keyed by the bit of their FALL inside the chunk.
-    constexpr int NCH = (T / 16 + kThreads - 1) / kThreads;
+    constexpr int NCH = (T / 16 + NT - 1) / NT;
     unsigned cmask[NCH], lmask[NCH];
     int cent[NCH];              // centre slot of the candidate found last in this thread's chunk (valid when it has exactly one)
     int tmax = -1;              // largest centre (shared-memory slot) of a complete short pulse
@@ -518,7 +527,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     bool have_long = false;
 #pragma unroll
     for (int ci = 0; ci < NCH; ci++) {
-        const int c = tid + ci * kThreads;
+        const int c = tid + ci * NT;
         cmask[ci] = 0;
         lmask[ci] = 0;
         cent[ci] = 0;
@@ -664,9 +673,9 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 
     // ---- per-warp candidate counts, edge flags, last pulse -> shared memory; the barrier that publishes them
     // also tells whether any run was deferred (rare), in which case the counts are redone after that pass ----
-    int (*s_cnt)[kWarps] = reinterpret_cast<int (*)[kWarps]>(sm.scratch + kScrCnt);
-    int *s_max = sm.scratch + kScrMax;
-    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + kScrFlag);
+    int (*s_cnt)[NW] = reinterpret_cast<int (*)[NW]>(sm.scratch + kScrCnt);
+    int *s_max = sm.scratch + scr_max(NW);
+    unsigned *s_flag = reinterpret_cast<unsigned *>(sm.scratch + scr_flag(NW));
     int wtot[NCH];
 #pragma unroll
     for (int ci = 0; ci < NCH; ci++) wtot[ci] = __reduce_add_sync(kFull, __popc(cmask[ci]));
@@ -682,9 +691,9 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     }
 
     // ---- long runs (rare): one warp per deferred fall ----
-    long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + kScrMaxLong);
+    long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + scr_max_long(NW));
     if (gb.sync_or(have_long)) {
-        for (int c = tid; c < T / 16; c += kThreads) {
+        for (int c = tid; c < T / 16; c += NT) {
             sm.xmask[c] = 0;
             sm.xlong[c] = 0;
         }
@@ -693,7 +702,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         const int n_slow = sm.scratch[kScrSlowN];
         const Access<FMT> X{P, sm.mag, w0, S};
         if (n_slow <= kSlowCap) {
-            for (int e = wid; e < n_slow; e += kWarps) {
+            for (int e = wid; e < n_slow; e += NW) {
                 const int kf = sm.slow[e];
                 long long p;
                 if (!resolve_long<FMT>(P, sm, w0, kf, lane, p)) continue;
@@ -709,7 +718,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             }
         } else {
             // more long runs than the deferral list holds: every warp rescans its own chunks
-            for (int c = wid; c < T / 16; c += kWarps) {
+            for (int c = wid; c < T / 16; c += NW) {
                 const int wq = kLeftHalo / 32 + (c >> 1);
                 const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
                 const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
@@ -743,7 +752,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         gb.sync();
 #pragma unroll
         for (int ci = 0; ci < NCH; ci++) {
-            const int c = tid + ci * kThreads;
+            const int c = tid + ci * NT;
             if (c < T / 16) {
                 cmask[ci] |= sm.xmask[c];
                 lmask[ci] |= sm.xlong[c];
@@ -769,7 +778,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 #pragma unroll
         for (int ci = 0; ci < NCH; ci++) {
             // lane q < 8 holds warp q's count: two warp reductions give this warp's offset and the row total
-            const int v = (lane < kWarps) ? s_cnt[ci][lane] : 0;
+            const int v = (lane < NW) ? s_cnt[ci][lane] : 0;
             const int before = wtot[ci] ? __reduce_add_sync(kFull, lane < wid ? v : 0) : 0;
             const int total = (ci + 1 < NCH) ? __reduce_add_sync(kFull, v) : 0;
             if (wtot[ci]) {
@@ -788,7 +797,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 }
                 int off = base + before + excl;
                 unsigned cm = cmask[ci];
-                const int k0 = kLeftHalo + (tid + ci * kThreads) * 16;
+                const int k0 = kLeftHalo + (tid + ci * NT) * 16;
                 if (cnt == 1 && lmask[ci] == 0) {
                     sm.list[off] = (unsigned short)cent[ci];        // centre kept since detection
                     cm = 0;
@@ -812,14 +821,14 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     if (tid < 32) {
         int v = 0;
 #pragma unroll
-        for (int ci = 0; ci < NCH; ci++) v += (lane < kWarps) ? s_cnt[ci][lane] : 0;
+        for (int ci = 0; ci < NCH; ci++) v += (lane < NW) ? s_cnt[ci][lane] : 0;
         n_cand = __reduce_add_sync(kFull, v);
     }
     if (tid == 0) {
         unsigned ff = 0;
         int mi = -1;
 #pragma unroll
-        for (int q = 0; q < kWarps; q++) {
+        for (int q = 0; q < NW; q++) {
             ff |= s_flag[q];
             mi = s_max[q] > mi ? s_max[q] : mi;
         }
@@ -844,11 +853,11 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 }
 
 // ---- phase 3 of one tile, by a group of n_warps warps (tid = thread index inside the group) -------------------
-template <int SPS, int FMT, class GB>
+template <int SPS, int FMT, int NT, class GB>
 __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const int tid,
                                            const int n_warps, const GB gb)
 {
-    using G = Geo<SPS>;
+    using G = Geo<SPS, NT>;
     constexpr int T = G::T;
     const int rh = SPS ? G::RH : P.rh;
     const int lane = tid & 31, wid = tid >> 5;
@@ -909,20 +918,21 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
 }
 
 // ---- the kernel: one CTA (8 warps) per tile, phases in sequence ---------------------------------------------
-template <int SPS, int FMT>
-__global__ void __launch_bounds__(kThreads, (Geo<SPS>::T <= 4096) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) scan_slice_kernel(const ScanParams P)
+template <int SPS, int FMT, int NT = kThreads>
+__global__ void __launch_bounds__(NT, ((Geo<SPS, NT>::T <= 16 * NT) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) * kThreads / NT)
+scan_slice_kernel(const ScanParams P)
 {
 #if defined(ADSB_HOST_EMU)
     unsigned char *smem_raw = cuda_emu::dynamic_smem();
 #else
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
-    const TileSmem sm = carve(smem_raw, Geo<SPS>::T, SPS ? Geo<SPS>::RH : P.rh);
+    const TileSmem sm = carve(smem_raw, Geo<SPS, NT>::T, SPS ? Geo<SPS, NT>::RH : P.rh);
     const long long tile = (long long)P.tile_first + blockIdx.x;
     const CtaBar gb;
-    scan_tile<SPS, FMT>(P, sm, tile, gb);
+    scan_tile<SPS, FMT, NT>(P, sm, tile, gb);
     gb.sync();
-    slice_tile<SPS, FMT>(P, sm, tile, (int)threadIdx.x, kWarps, gb);
+    slice_tile<SPS, FMT, NT>(P, sm, tile, (int)threadIdx.x, NT / 32, gb);
 }
 
 }  // namespace adsb

@@ -16,6 +16,7 @@ el "variants rc=$?"
 BESTFULL=$(cat gpurun_out/best_variant.txt 2>/dev/null || echo base)
 BEST=${BESTFULL%@*}
 if [ "$BEST" != "$BESTFULL" ]; then export ADSB_PREFETCH_TILES=${BESTFULL#*@}; fi
+if [ "${BEST%\%*}" != "$BEST" ]; then export ADSB_SCAN_THREADS=${BEST#*%}; BEST=${BEST%\%*}; fi
 export ADSB_B200_LIB=$PWD/gr_adsb_b200/csrc/variants/libadsb_$BEST.so
 el "best=$BESTFULL"
 timeout 220 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_best.json 2> gpurun_out/bench_best.log

@@ -30,6 +30,9 @@ def _defs(*on):
 
 VARIANTS = {
     "default": _defs(),
+    # the scan kernel also instantiated for 128- and 512-thread CTAs (tiles of 2048 / 8192 samples at 2 Msps):
+    # run as "nt%128" / "nt%512" (ADSB_SCAN_THREADS); "nt" alone is the 256-thread kernel of this build
+    "nt": _defs() + ["-DADSB_SCAN_NT_VARIANTS=1"],
 }
 
 
@@ -177,10 +180,14 @@ def run(names, log2n, iters, write_best=True):
     results = []
     for name in names:
         # "variant@N": the same library with the L2 prefetch distance set to N tiles (ADSB_PREFETCH_TILES)
+        # "variant%T": the same library with T threads per scan CTA (ADSB_SCAN_THREADS, needs an "nt" build)
         vname, _, pf = name.partition("@")
+        vname, _, nt = vname.partition("%")
         env = dict(os.environ, ADSB_B200_LIB=lib_of(vname))
         if pf:
             env["ADSB_PREFETCH_TILES"] = pf
+        if nt:
+            env["ADSB_SCAN_THREADS"] = nt
         t0 = time.time()
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "one", name, str(log2n), str(iters)], env=env,
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
