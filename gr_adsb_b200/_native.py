@@ -80,6 +80,11 @@ def lib():
     if not os.path.isfile(LIB_PATH):
         raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
+    if hasattr(L, "adsb_host_emulation_marker") and os.environ.get("ADSB_EMU") != "1":
+        # tests/emu builds the CUDA sources for the host to check kernel logic without a GPU; that library is test
+        # infrastructure and must never serve as the product path
+        raise RuntimeError("%s is the host-emulation TEST library (tests/emu); it only loads in ADSB_EMU=1 test runs"
+                           % LIB_PATH)
     vp, sz, i64, f32, i32 = C.c_void_p, C.c_size_t, C.c_int64, C.c_float, C.c_int
     L.adsb_strerror.restype = C.c_char_p
     L.adsb_strerror.argtypes = [i32]

@@ -356,3 +356,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 }
 
 }  // namespace cuda_emu
+
+// Marks this shared library as the host emulation: gr_adsb_b200/_native.py refuses to load a library exporting
+// this symbol unless the test switch ADSB_EMU=1 is set, so the package cannot end up computing on the CPU by accident.
+extern "C" int adsb_host_emulation_marker(void) { return 1; }

@@ -75,3 +75,18 @@ def test_synth_crc_roundtrip():
     m[:, 40] ^= 1
     assert np.all(synth.crc24_syndrome(m) != 0)
     assert synth.bits_to_hex(synth.hex_to_bits("8D4840D6202CC371C32CE0576098")) == "8D4840D6202CC371C32CE0576098"
+
+
+def test_emulation_library_is_refused_outside_test_mode(tmp_path):
+    """The host-emulation build of the kernels (tests/emu) is test infrastructure: the package must not load it as
+    its compute path unless the test switch ADSB_EMU=1 is set."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import build_emu
+    lib = build_emu.build()
+    code = "import gr_adsb_b200 as g; g.Context(2, 1 << 16)"
+    env = dict(os.environ, ADSB_B200_LIB=lib)
+    env.pop("ADSB_EMU", None)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode != 0 and "host-emulation TEST library" in r.stdout
