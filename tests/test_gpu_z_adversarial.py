@@ -7,6 +7,7 @@ float32 |IQ|^2 input and for complex64 IQ input (where the dense pre-filter comp
 subtraction and leans on the device's canonical NaN)."""
 import numpy as np
 import pytest
+from hypothesis import given, settings, strategies as st
 
 import golden_io as G
 import gr_adsb_b200 as g
@@ -155,4 +156,32 @@ def test_hundreds_of_long_runs_per_tile(sps):
     ref = co.run_stream(x, sps * 1e6, 0.01, None, cap=n + 8)
     ctx = ctx_for(sps, n)
     hits = ctx.burst_work(x, threshold=0.01)
+    check(hits, sps, ref, ctx)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2**31 - 1), st.sampled_from([2, 2, 2, 4, 8, 6]), st.sampled_from([0.01, 0.01, 0.004, 0.02, 1e-3]),
+       st.booleans())
+def test_fast_path_adversarial_random(seed, sps, thr, complex_input):
+    """The two generators above under hypothesis-drawn seeds, rates and thresholds."""
+    rng = np.random.default_rng(seed)
+    T = 4096 if sps in (2, 4) else 8192
+    n = int(rng.integers(3, 7)) * T + int(rng.integers(0, T))
+    if complex_input:
+        design = adversarial_mag(n, sps, thr, rng, [0.0, 1e-42, 3e38, 0.25])
+        with np.errstate(all="ignore"):
+            amp = np.sqrt(design).astype(np.float32)
+        ph = rng.uniform(0, 2 * np.pi, n).astype(np.float32)
+        ph[rng.random(n) < 0.5] = 0.0
+        buf = (amp * np.cos(ph) + 1j * amp * np.sin(ph)).astype(np.complex64)
+        idx = rng.integers(0, n, n // 400)
+        buf[idx] = rng.choice(np.array([np.nan, np.inf, 1j * np.inf, 3e19 + 3e19j], np.complex64), len(idx))
+        with np.errstate(all="ignore"):
+            x = co.mag2(buf)
+    else:
+        buf = x = adversarial_mag(n, sps, thr, rng, [np.nan, np.inf, 0.0, 1e-42, -1.0, 3e38])
+    with np.errstate(all="ignore"):
+        ref = co.run_stream(x, sps * 1e6, thr, None, cap=n + 8)
+    ctx = ctx_for(sps, n)
+    hits = ctx.burst_work(buf, threshold=thr)
     check(hits, sps, ref, ctx)
