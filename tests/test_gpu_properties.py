@@ -3,7 +3,7 @@ negatives, inf, nan, subnormal-range thresholds) -- whole-buffer fused entry poi
 (-0.0 is left out: NumPy's median of a window holding both zeros may return either sign.)"""
 import numpy as np
 import pytest
-from hypothesis import given, settings, strategies as st
+from hypothesis import HealthCheck, given, settings, strategies as st
 
 import golden_io as G
 import gr_adsb_b200 as g
@@ -53,7 +53,7 @@ def streams(draw):
     return x, sps, thr
 
 
-@settings(max_examples=250, deadline=None)
+@settings(max_examples=250, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(streams())
 def test_fused_whole_buffer_equals_oracle(case):
     x, sps, thr = case
@@ -68,7 +68,7 @@ def test_fused_whole_buffer_equals_oracle(case):
     assert ctx_for.__globals__["_ctx"][sps].get_state()[1] == ref["state"][1]
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(streams(), st.sampled_from([1, 7, 64, 100, 333, 2048]))
 def test_blocks_per_call_equal_oracle(case, chunk):
     x, sps, thr = case

@@ -7,7 +7,7 @@ float32 |IQ|^2 input and for complex64 IQ input (where the dense pre-filter comp
 subtraction and leans on the device's canonical NaN)."""
 import numpy as np
 import pytest
-from hypothesis import given, settings, strategies as st
+from hypothesis import HealthCheck, given, settings, strategies as st
 
 import golden_io as G
 import gr_adsb_b200 as g
@@ -159,7 +159,7 @@ def test_hundreds_of_long_runs_per_tile(sps):
     check(hits, sps, ref, ctx)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(st.integers(0, 2**31 - 1), st.sampled_from([2, 2, 2, 4, 8, 6]), st.sampled_from([0.01, 0.01, 0.004, 0.02, 1e-3]),
        st.booleans())
 def test_fast_path_adversarial_random(seed, sps, thr, complex_input):
