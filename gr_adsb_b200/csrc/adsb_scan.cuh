@@ -5,8 +5,9 @@
 //   phase 1  HBM -> registers -> |IQ|^2 -> shared memory, threshold bitmap by warp ballot
 //   phase 2  bitmap -> falling edges -> pulse centres (bit-parallel for runs <= LMAX samples),
 //            dense 3-tap pre-filter, full 16-tap preamble test on the survivors
-//   phase 3  one warp per candidate: exact median of the 100-sample noise window (register bitonic
-//            sort), 112 PPM decisions by ballot, CRC-24 by XOR-reduction
+//   phase 3  candidates in pairs, two tasks per pair spread over the warps: exact medians of the two 100-sample
+//            noise windows (one per half-warp: register sorting network + selection of the two middle ranks), and
+//            2 x 112 PPM decisions by ballot with CRC-24 by XOR-reduction; edge tiles: one warp per candidate
 // Interior tiles of the specialised sample rates (2, 4, 8 samples/symbol) take the fast paths; tiles
 // touching the window edges, and other rates, take a generic per-edge path with identical results.
 #pragma once
