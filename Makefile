@@ -19,7 +19,11 @@ test-cpu:
 test-gpu:
 	python -m pytest tests -x -q -m gpu
 
-clean:
-	rm -f $(LIB) oracle/liboracle_adsb.so
+# the gpu parity tests against the host emulation of the CUDA sources (tests/emu): a logic check without a GPU
+test-emu:
+	ADSB_EMU=1 python -m pytest tests -x -q -m gpu
 
-.PHONY: all test-cpu test-gpu clean
+clean:
+	rm -f $(LIB) oracle/liboracle_adsb.so tests/emu/libadsb_emu*.so
+
+.PHONY: all test-cpu test-gpu test-emu clean
