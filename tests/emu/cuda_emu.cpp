@@ -212,6 +212,16 @@ void guarded_free(void *p)
     free(static_cast<unsigned char *>(p) - kGuard);
 }
 
+// A thread in a wait loop gives way to the others.  A block whose threads only ever yield is a livelock.
+static unsigned long long g_yields = 0;
+void yield()
+{
+    if (++g_yields > 200000000ULL) die("livelock: threads keep spinning without reaching a collective or returning");
+    Fiber *f = g_cur;
+    f->wait_gen = nullptr;
+    switch_to(&f->ctx, &g_sched);
+}
+
 int lane_id() { return g_cur->lane; }
 unsigned char *dynamic_smem() { return g_smem; }
 
@@ -295,6 +305,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
                 g_blockIdx.x = bx;
                 g_blockIdx.y = by;
                 g_blockIdx.z = bz;
+                g_yields = 0;
                 memset(g_smem, 0xA5, smem_bytes);      // uninitialised shared memory is not zero
                 memset(g_smem + smem_bytes, kCanary, kGuard);
                 for (unsigned w = 0; w < n_warps; w++) {

@@ -48,6 +48,7 @@ uint64_t *warp_exchange(int op, unsigned mask, uint64_t v, unsigned *present);
 int block_barrier(int pred, int mode);
 int lane_id();
 unsigned char *dynamic_smem();
+void yield();                     // a spinning thread lets the others run (stands in for __nanosleep in wait loops)
 }  // namespace cuda_emu
 
 #define threadIdx (cuda_emu::g_threadIdx)
@@ -152,6 +153,9 @@ static inline long long max(long long a, long long b) { return a > b ? a : b; }
 
 // ---- atomics (fibers never pre-empt each other) ------------------------------------------------------------------
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+static inline int atomicCAS(int *p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
+static inline void __threadfence_block() {}
+static inline void __threadfence() {}
 static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline long long atomicMax(long long *p, long long v) { long long o = *p; if (v > o) *p = v; return o; }
