@@ -248,18 +248,6 @@ cudaError_t launch_scan_s(int sps, const ScanParams &P, int fmt, unsigned n_bloc
     }
 }
 
-// threads per CTA of the scan kernel: 256; A/B builds (-DADSB_SCAN_NT_VARIANTS) also carry 128 and 512, picked per
-// context with ADSB_SCAN_THREADS
-int scan_threads_from_env()
-{
-#ifdef ADSB_SCAN_NT_VARIANTS
-    const char *e = getenv("ADSB_SCAN_THREADS");
-    const int nt = e ? atoi(e) : kThreads;
-    if (nt == 128 || nt == 512) return nt;
-#endif
-    return kThreads;
-}
-
 cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned tile_first, unsigned n_blocks, cudaStream_t s)
 {
     if (n_blocks == 0) return cudaSuccess;
@@ -267,13 +255,7 @@ cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned til
     P.tile_first = tile_first;
     P.n_tiles_launch = n_blocks;
     bool *configured = &c->scan_configured[fmt];
-    switch (c->nt) {
-#ifdef ADSB_SCAN_NT_VARIANTS
-    case 128: return launch_scan_s<128>(c->sps, P, fmt, n_blocks, s, configured);
-    case 512: return launch_scan_s<512>(c->sps, P, fmt, n_blocks, s, configured);
-#endif
-    default: return launch_scan_s<kThreads>(c->sps, P, fmt, n_blocks, s, configured);
-    }
+    return launch_scan_s<kThreads>(c->sps, P, fmt, n_blocks, s, configured);
 }
 
 long long tiles_for(const adsb_ctx *c, long long n_out, long long lead)
@@ -521,7 +503,7 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     ctx->device = device;
     ctx->sps = sps;
     ctx->hist = 8 * sps - 1;
-    ctx->nt = scan_threads_from_env();
+    ctx->nt = kThreads;
     ctx->T = tile_items(sps, ctx->nt);
     ctx->rh = right_halo(sps, ctx->nt);
     ctx->max_items = max_items;

@@ -18,9 +18,6 @@ namespace adsb {
 #ifndef ADSB_MIN_CTAS_BIG
 #define ADSB_MIN_CTAS_BIG 4  // same for the 8192-sample tile kernels (8 Msps and unspecialised rates)
 #endif
-#ifndef ADSB_OPT_SLICE_QUEUE
-#define ADSB_OPT_SLICE_QUEUE 0 // A/B switch: warps commit their candidates in order and slice from a shared-memory queue
-#endif                         // (no CTA barrier between detection and slicing); not yet timed on the device
 #ifndef ADSB_LMAX2
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
@@ -109,21 +106,6 @@ __host__ __device__ constexpr int scr_max(int nw) { return kScrCnt + 2 * nw; }
 __host__ __device__ constexpr int scr_flag(int nw) { return kScrCnt + 3 * nw; }
 __host__ __device__ constexpr int scr_max_long(int nw) { return kScrCnt + 4 * nw; }
 
-#if ADSB_OPT_SLICE_QUEUE
-// queue cells in the scratch area (they take the place of the per-warp count / flag cells)
-enum { kQTurn = 16, kQTail = 17, kQHead = 18, kQDone = 19, kQGoff = 20, kQFlag = 21, kQMax = 22, kQMaxLong = 24 /* long long */ };
-
-__device__ __forceinline__ void spin_pause()
-{
-#if defined(ADSB_HOST_EMU)
-    cuda_emu::yield();
-#else
-    __nanosleep(40);
-#endif
-}
-__device__ __forceinline__ int vload(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
-__device__ __forceinline__ void vstore(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
-#endif
 
 // ---- thread-group barrier: scan_tile / slice_tile are written against this interface so that the phases can
 // be moved to warp groups with named barriers; a persistent 8+4-warp producer/consumer variant was measured in
@@ -427,16 +409,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 
     if (tid == 0) {
         sm.scratch[kScrSlowN] = 0;
-#if ADSB_OPT_SLICE_QUEUE
-        sm.scratch[kQTurn] = 0;
-        sm.scratch[kQTail] = 0;
-        sm.scratch[kQHead] = 0;
-        sm.scratch[kQDone] = 0;
-        sm.scratch[kQGoff] = (int)((unsigned)tile * kTileSlots);
-        sm.scratch[kQFlag] = 0;
-        sm.scratch[kQMax] = -1;
-        *reinterpret_cast<long long *>(sm.scratch + kQMaxLong) = -1;
-#endif
     }
     const long long a0 = tile * T;                 // array index of the tile's first owned sample
     const long long w0 = a0 + P.lead - kLeftHalo;  // window index of shared-memory slot 0
@@ -555,18 +527,12 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     int tmax = -1;              // largest centre (shared-memory slot) of a complete short pulse
     unsigned tflags = 0;
     bool have_long = false;
-#if ADSB_OPT_SLICE_QUEUE
-    unsigned longfs[NCH];
-#endif
 #pragma unroll
     for (int ci = 0; ci < NCH; ci++) {
         const int c = tid + ci * NT;
         cmask[ci] = 0;
         lmask[ci] = 0;
         cent[ci] = 0;
-#if ADSB_OPT_SLICE_QUEUE
-        longfs[ci] = 0;
-#endif
         if (c >= T / 16) continue;
         const int wq = kLeftHalo / 32 + (c >> 1);
         const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
@@ -693,9 +659,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 }
             }
         }
-#if ADSB_OPT_SLICE_QUEUE
-        longfs[ci] = longf;              // resolved by this warp itself right after the loop
-#else
         if (longf) {
             have_long = true;
             unsigned lf = longf;
@@ -706,133 +669,10 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 if (slot < kSlowCap) sm.slow[slot] = (unsigned short)(k0 + b);
             }
         }
-#endif
         cmask[ci] = cm;
         lmask[ci] = lm;
     }
 
-#if ADSB_OPT_SLICE_QUEUE
-    (void)have_long;
-    // ---- long runs that leave the staged span (rare): resolved by the owning warp itself, all lanes cooperating ----
-    long long wmax_long = -1;
-    {
-        const Access<FMT> X{P, sm.mag, w0, S};
-#pragma unroll
-        for (int ci = 0; ci < NCH; ci++) {
-            unsigned any = __ballot_sync(kFull, longfs[ci] != 0);
-            while (any) {
-                const int src = __ffs(any) - 1;
-                any &= any - 1;
-                unsigned m = __shfl_sync(kFull, longfs[ci], src);
-                const int k0s = kLeftHalo + ((wid * 32 + src) + ci * NT) * 16;
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    long long p;
-                    if (!resolve_long<FMT>(P, sm, w0, k0s + b, lane, p)) continue;
-                    const bool mt = warp_match<FMT>(X, p, h, lane);
-                    wmax_long = p > wmax_long ? p : wmax_long;
-                    if (mt && lane == src) {
-                        cmask[ci] |= 1u << b;
-                        lmask[ci] |= 1u << b;
-                    }
-                }
-            }
-        }
-    }
-    // ---- edge flags / last pulse of the tile: shared-memory atomics, read by the warp that commits last ----
-    {
-        const unsigned f = __reduce_or_sync(kFull, tflags);
-        const int m = __reduce_max_sync(kFull, tmax);
-        if (lane == 0) {
-            if (f) atomicOr(reinterpret_cast<unsigned *>(sm.scratch + kQFlag), f);
-            if (m >= 0) atomicMax(sm.scratch + kQMax, m);
-            if (wmax_long >= 0) atomicMax(reinterpret_cast<long long *>(sm.scratch + kQMaxLong), wmax_long);
-        }
-    }
-    // ---- ordered commit: the (chunk row, warp) pairs append their candidates to sm.list in turn, so the list is in
-    // ascending sample order without any warp needing another warp's count; a warp that has committed goes on to
-    // slice whatever is listed already (slice_queue) instead of waiting at a barrier for the slower warps ----
-#pragma unroll
-    for (int ci = 0; ci < NCH; ci++) {
-        const int cnt = __popc(cmask[ci]);
-        const int wt = __reduce_add_sync(kFull, cnt);
-        const unsigned has = __ballot_sync(kFull, cnt != 0);
-        int excl = __popc(has & ((1u << lane) - 1u));
-        if (wt != __popc(has)) {
-            int inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(kFull, inc, d);
-                if (lane >= d) inc += t;
-            }
-            excl = inc - cnt;
-        }
-        const int turn = ci * NW + wid;
-        int base = 0;
-        if (lane == 0) {
-            while (vload(sm.scratch + kQTurn) != turn) spin_pause();
-            base = vload(sm.scratch + kQTail);
-        }
-        base = __shfl_sync(kFull, base, 0);
-        if (cnt) {
-            int off = base + excl;
-            unsigned cm = cmask[ci];
-            const int k0 = kLeftHalo + (tid + ci * NT) * 16;
-            if (cnt == 1 && lmask[ci] == 0) {
-                sm.list[off] = (unsigned short)cent[ci];
-                cm = 0;
-            }
-            while (cm) {
-                const int b = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const int kf = k0 + b;
-                unsigned short ent = (unsigned short)(kf | 0x8000);
-                if (!((lmask[ci] >> b) & 1u)) {
-                    const int r = walk_back_smem(sm.bits, kf);
-                    ent = (unsigned short)((r + kf) >> 1);
-                }
-                sm.list[off++] = ent;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            const int n_now = base + wt;
-            if (turn == NCH * NW - 1) {
-                // last commit of the tile: global bookkeeping, then release the tail of the queue
-                const int n_cand = n_now;
-                unsigned off = (unsigned)tile * kTileSlots;
-                if (n_cand > kTileSlots) {
-                    off = (unsigned)P.n_tiles_total * kTileSlots + (unsigned)atomicAdd(&P.hdr->n_cand, (unsigned long long)n_cand);
-                    vstore(sm.scratch + kQGoff, (int)off);
-                }
-                const unsigned ff = (unsigned)vload(sm.scratch + kQFlag);
-                const int mi = vload(sm.scratch + kQMax);
-                const long long ml = *reinterpret_cast<volatile long long *>(sm.scratch + kQMaxLong);
-                long long mm = (mi >= 0) ? (w0 + mi) : -1;
-                mm = ml > mm ? ml : mm;
-                if (ff) atomicOr(&P.hdr->flags, ff);
-                if (mm >= 0) atomicMax(&P.hdr->last_pulse, mm);
-                P.tile_tab[tile] = make_uint2(off, (unsigned)n_cand);
-                if (n_cand > 0) atomicAdd(&P.tile_chunk_tot[tile / kThreads], (unsigned)n_cand);
-                const long long kl = (P.own_hi - 1) - w0;
-                if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
-                vstore(sm.scratch + kQTail, n_now);
-                if (n_cand > kTileSlots) vstore(sm.scratch + kQHead, 0);     // the whole tile is redone into the overflow block
-                __threadfence_block();
-                vstore(sm.scratch + kQDone, 1);
-            } else {
-                vstore(sm.scratch + kQTail, n_now);
-            }
-            __threadfence_block();
-            vstore(sm.scratch + kQTurn, turn + 1);
-        }
-        __syncwarp();
-    }
-}
-
-#else
     // ---- per-warp candidate counts, edge flags, last pulse -> shared memory; the barrier that publishes them
     // also tells whether any run was deferred (rare), in which case the counts are redone after that pass ----
     int (*s_cnt)[NW] = reinterpret_cast<int (*)[NW]>(sm.scratch + kScrCnt);
@@ -1013,7 +853,6 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         if (kl >= kLeftHalo && kl < kLeftHalo + T) P.hdr->x_last = sm.mag[kl];
     }
 }
-#endif
 
 // ---- phase 3 of one tile, by a group of n_warps warps (tid = thread index inside the group) -------------------
 template <int SPS, int FMT, int NT, class GB>
@@ -1027,14 +866,10 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     const int S = kLeftHalo + T + rh;
     const int h = SPS ? G::H : (P.sps >> 1);
     const long long w0 = tile * T + P.lead - kLeftHalo;
-#if !ADSB_OPT_SLICE_QUEUE
     const int n_cand = sm.scratch[kScrNCand];
     if (n_cand == 0) return;
     const bool fast = sm.scratch[kScrFast] != 0;
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
-#else
-    const bool fast = SPS != 0 && ((unsigned)tile - P.fast_lo) <= P.fast_span && P.fast_span != 0xffffffffu;
-#endif
 
     // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
     // interior tiles: candidates go in pairs (half-warp each) and every pair is two tasks -- median/SNR and
@@ -1043,49 +878,9 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     const int sps_rt = SPS ? SPS : P.sps;
     // records go straight to this tile's block of the candidate array (the two tasks of a pair fill
     // disjoint fields), so no staging buffer and no barrier after the slicing
-#if ADSB_OPT_SLICE_QUEUE
-    // tasks come from the queue the committing warps fill (scan_tile): lane 0 claims the next task as soon as its
-    // pair of candidates is listed; while some warp is still detecting only complete pairs inside the tile's fixed
-    // record block are handed out, the rest (an odd last candidate, a tile that overflows its block and is redone
-    // into the overflow area) once the last warp has committed
-    (void)wid;
-    (void)n_warps;
-    for (;;) {
-        int t = -1, n_cand = 0;
-        if (lane == 0) {
-            for (;;) {
-                const int done = vload(sm.scratch + kQDone);
-                __threadfence_block();
-                const int tail = vload(sm.scratch + kQTail);
-                const int head = vload(sm.scratch + kQHead);
-                int limit = tail;
-                if (!done) {
-                    limit &= ~1;
-                    if (limit > kTileSlots) limit = kTileSlots;
-                }
-                if (head < ((limit + 1) >> 1) * 2) {
-                    if (atomicCAS(sm.scratch + kQHead, head, head + 1) == head) {
-                        t = head;
-                        n_cand = limit;
-                        break;
-                    }
-                    continue;
-                }
-                if (done) break;
-                spin_pause();
-            }
-        }
-        t = __shfl_sync(kFull, t, 0);
-        n_cand = __shfl_sync(kFull, n_cand, 0);
-        if (t < 0) break;
-        __threadfence_block();
-        const unsigned g_off = (unsigned)vload(sm.scratch + kQGoff);
-        const int c = (t >> 1) * 2;
-#else
     const int n_tasks = ((n_cand + 1) >> 1) * 2;
     for (int t = wid; t < n_tasks; t += n_warps) {
         const int c = (t >> 1) * 2;
-#endif
         const bool two = c + 1 < n_cand;
         const unsigned e0 = sm.list[c];
         const unsigned e1 = two ? sm.list[c + 1] : e0;
@@ -1138,9 +933,7 @@ scan_slice_kernel(const ScanParams P)
     const long long tile = (long long)P.tile_first + blockIdx.x;
     const CtaBar gb;
     scan_tile<SPS, FMT, NT>(P, sm, tile, gb);
-#if !ADSB_OPT_SLICE_QUEUE
     gb.sync();
-#endif
     slice_tile<SPS, FMT, NT>(P, sm, tile, (int)threadIdx.x, NT / 32, gb);
 }
 

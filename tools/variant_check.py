@@ -21,7 +21,7 @@ CSRC = os.path.join(ROOT, "gr_adsb_b200", "csrc")
 VDIR = os.path.join(CSRC, "variants")
 
 # compile-time switches currently under test (adsb_scan.cuh / adsb_device.cuh); "default" = the source as it is
-_OPTS = ["SLICE_QUEUE"]     # blocks guarded by `#if ADSB_OPT_<name>` in csrc/
+_OPTS = []     # blocks guarded by `#if ADSB_OPT_<name>` in csrc/
 
 
 def _defs(*on):
@@ -30,12 +30,6 @@ def _defs(*on):
 
 VARIANTS = {
     "default": _defs(),
-    # the scan kernel also instantiated for 128- and 512-thread CTAs (tiles of 2048 / 8192 samples at 2 Msps):
-    # run as "nt%128" / "nt%512" (ADSB_SCAN_THREADS); "nt" alone is the 256-thread kernel of this build
-    "nt": _defs() + ["-DADSB_SCAN_NT_VARIANTS=1"],
-    # ordered commit + shared-memory task queue between detection and slicing (no CTA barrier there)
-    "queue": _defs("SLICE_QUEUE"),
-    "queuent": _defs("SLICE_QUEUE") + ["-DADSB_SCAN_NT_VARIANTS=1"],
 }
 
 
