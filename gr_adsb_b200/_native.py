@@ -23,6 +23,9 @@ HIT_FEC_FIXED = 0x8
 FEC_NONE, FEC_CONSERVATIVE = 0, 1
 FMT_F32, FMT_C64, FMT_SC16, FMT_CU8 = 0, 1, 2, 3
 CARRY_USED_ON_DEVICE = -(1 << 63)
+E_PEER = -8
+SHARD_CTRL_BYTES, IPC_HANDLE_BYTES = 8192, 64
+SHARD_PH_SIGNAL, SHARD_PH_SCAN, SHARD_PH_EXPORT, SHARD_PH_PLAN, SHARD_PH_CHECK, SHARD_PH_ALL = 1, 2, 4, 8, 16, 31
 
 HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
 assert HIT_DTYPE.itemsize == 32
@@ -63,7 +66,8 @@ EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_creat
            "adsb_framer_work", "adsb_demod_work", "adsb_burst_work", "adsb_burst_work_dev", "adsb_burst_finish",
            "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
            "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev", "adsb_set_error_correction",
-           "adsb_burst_mag_out"]
+           "adsb_burst_mag_out", "adsb_shard_alloc", "adsb_shard_attach", "adsb_shard_attach_ptrs", "adsb_shard_detach",
+           "adsb_shard_write", "adsb_shard_step"]
 
 
 def lib():
@@ -124,6 +128,18 @@ def lib():
     L.adsb_burst_export_carry_dev.argtypes = [vp, i64, vp, vp]
     L.adsb_burst_carry_round_dev.restype = i32
     L.adsb_burst_carry_round_dev.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.adsb_shard_alloc.restype = i32
+    L.adsb_shard_alloc.argtypes = [vp, sz, C.POINTER(vp), vp]
+    L.adsb_shard_attach.restype = i32
+    L.adsb_shard_attach.argtypes = [vp, i32, i32, vp]
+    L.adsb_shard_attach_ptrs.restype = i32
+    L.adsb_shard_attach_ptrs.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.adsb_shard_detach.restype = i32
+    L.adsb_shard_detach.argtypes = [vp]
+    L.adsb_shard_write.restype = i32
+    L.adsb_shard_write.argtypes = [vp, sz, vp, sz, vp]
+    L.adsb_shard_step.restype = i32
+    L.adsb_shard_step.argtypes = [vp, i32, sz, f32, i32, i32, vp]
     L.adsb_profile_enable.restype = i32
     L.adsb_profile_enable.argtypes = [vp, i32]
     L.adsb_profile_last.restype = i32
@@ -287,6 +303,36 @@ class Context(object):
     def burst_carry_round_dev(self, gathered_ptr, world, rank, final_check=False, stream=0):
         self._check(lib().adsb_burst_carry_round_dev(self._h, C.c_void_p(gathered_ptr), int(world), int(rank),
                                                       1 if final_check else 0, C.c_void_p(stream)))
+
+    # --- multi-GPU peer mode (include/adsb_b200.h: adsb_shard_*) -----------------------------------------
+    def shard_alloc(self, sample_bytes):
+        """-> (device pointer of the sample area, 64-byte CUDA IPC handle of the allocation)"""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(lib().adsb_shard_alloc(self._h, int(sample_bytes), C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def shard_attach(self, rank, world, handles):
+        """handles: the `world` IPC handles (bytes, rank order) exchanged by any transport"""
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        assert len(blob) == world * IPC_HANDLE_BYTES
+        self._check(lib().adsb_shard_attach(self._h, int(rank), int(world), C.c_char_p(blob)))
+
+    def shard_attach_ptrs(self, rank, world, sample_ptrs):
+        """Ranks living in one process: `sample_ptrs[r]` = what rank r's shard_alloc returned."""
+        arr = (C.c_void_p * world)(*[int(p) - SHARD_CTRL_BYTES for p in sample_ptrs])
+        self._check(lib().adsb_shard_attach_ptrs(self._h, int(rank), int(world), arr))
+
+    def shard_detach(self):
+        self._check(lib().adsb_shard_detach(self._h))
+
+    def shard_write(self, src_ptr, nbytes, byte_offset=0, stream=None):
+        self._check(lib().adsb_shard_write(self._h, int(byte_offset), C.c_void_p(int(src_ptr)), int(nbytes),
+                                           C.c_void_p(stream) if stream else None))
+
+    def shard_step(self, fmt, shard_items, threshold, phases=SHARD_PH_ALL, use_graph=False, stream=0):
+        self._check(lib().adsb_shard_step(self._h, int(fmt), int(shard_items), float(np.float32(threshold)), int(phases),
+                                          1 if use_graph else 0, C.c_void_p(stream)))
 
     # --- measurement hook ------------------------------------------------------------------------------
     def profile_enable(self, on=True):

@@ -38,6 +38,13 @@ class _DeviceBlock(object):
             self._ctx = new
         return self._ctx
 
+    def close(self):
+        """Release the device buffers now (otherwise when the block is garbage collected)."""
+        ctx = getattr(self, "_ctx", None)
+        if ctx is not None:
+            ctx.close()
+            self._ctx = None
+
 
 class framer(gr.sync_block, _DeviceBlock):
     """ADS-B Framer: burst detection, emits "burst" stream tags ("SOB", snr)."""

@@ -16,6 +16,7 @@ using namespace adsb;
 
 static_assert(sizeof(adsb_hit) == sizeof(Rec), "adsb_hit layout");
 static_assert(kTilesPerChunk == kThreads, "K1 accumulates tile_chunk_tot[tile / kThreads]");
+static_assert(ADSB_SHARD_MAX_WORLD == kMaxWorld, "header and kernels agree on the largest world");
 
 namespace {
 
@@ -104,6 +105,25 @@ struct adsb_ctx {
     int staged_fmt;              // format / item count of the input adsb_burst_work staged last (-1: none)
     size_t staged_n;
     bool scan_configured[kNumFmt];  // per sample format: shared-memory attributes of the scan kernel set on this device
+    // multi-GPU peer mode (adsb_shard_*): symmetric allocation [ShardCtrl | samples] of every rank, mapped here
+    struct {
+        int rank, world;         // world == 0: not attached
+        void *own_base;          // this rank's allocation (adsb_shard_alloc); null when the caller brought its own
+        size_t own_bytes;
+        void *peer_base[kMaxWorld];   // every rank's allocation as seen from this device (own entry included)
+        bool ipc_opened[kMaxWorld];
+#if !defined(ADSB_HOST_EMU)
+        cudaGraphExec_t exec;    // the captured step (null: none)
+        cudaGraph_t graph;
+#endif
+        struct {
+            int fmt, phases;
+            size_t items;
+            float thr;
+            cudaStream_t stream;
+        } key;                   // what `exec` was captured for
+        unsigned long long steps_graph, steps_plain;
+    } shard;
     Rec *h_tmp;                  // host scratch of the two-block entry points
     size_t h_tmp_cap;
     unsigned char *h_bits;
@@ -285,6 +305,7 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
     P.n_arr = (long long)n_in;
     P.lead = (long long)lead;
     P.n_loc = (long long)(lead + n_in);
+    P.win_hi = P.n_loc;        // no neighbours: in_left / in_right stay null
     P.own_lo = (long long)halo_left;
     P.own_hi = (long long)n_out;
     P.base = base;
@@ -416,6 +437,7 @@ long long next_eob(const Header &h, long long eob_in, long long n_out, int sps)
 
 int status_of(adsb_ctx *ctx, const Header &h)
 {
+    if (h.flags & kFlagPeerTimeout) return fail(ctx, ADSB_E_PEER, "a neighbouring rank did not reach the step (peer wait timed out)");
     if (h.flags & kFlagHalo) return fail(ctx, ADSB_E_HALO, "pulse run crosses the left halo edge");
     if (h.flags & (kFlagCandOverflow | kFlagHitOverflow)) return fail(ctx, ADSB_E_NOMEM, "candidate capacity exceeded (raise max_items)");
     return ADSB_OK;
@@ -436,6 +458,7 @@ const char *adsb_strerror(int code)
     case ADSB_E_CAPACITY: return "output capacity too small";
     case ADSB_E_NODEVICE: return "no usable sm_100 CUDA device";
     case ADSB_E_HALO: return "pulse run crosses the left halo of a shard";
+    case ADSB_E_PEER: return "multi-GPU peer exchange failed";
     case ADSB_E_INTERNAL: return "internal error";
     default: return "unknown error";
     }
@@ -457,6 +480,8 @@ void adsb_destroy(adsb_ctx *ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    adsb_shard_detach(ctx);
+    if (ctx->shard.own_base) cudaFree(ctx->shard.own_base);
     cudaFree(ctx->d_in);
     cudaFree(ctx->d_cand);
     cudaFree(ctx->d_ord);
@@ -711,6 +736,246 @@ int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_o
     return ADSB_OK;
 }
 
+// ---- multi-GPU peer mode -----------------------------------------------------------------------------------
+int adsb_shard_alloc(adsb_ctx *ctx, size_t sample_bytes, void **d_samples, void *ipc_handle)
+{
+    if (!ctx || !d_samples || sample_bytes == 0) return ADSB_E_INVAL;
+    ON_DEVICE(ctx);
+    if (ctx->shard.world) return fail(ctx, ADSB_E_INVAL, "adsb_shard_alloc: detach first");
+    if (ctx->shard.own_base) {
+        cudaFree(ctx->shard.own_base);
+        ctx->shard.own_base = nullptr;
+    }
+    const size_t bytes = ADSB_SHARD_CTRL_BYTES + ((sample_bytes + 255) & ~(size_t)255);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, "cudaMalloc(shard)", e);
+    CK(cudaMemset(p, 0, ADSB_SHARD_CTRL_BYTES));
+    ctx->shard.own_base = p;
+    ctx->shard.own_bytes = bytes;
+    *d_samples = static_cast<char *>(p) + ADSB_SHARD_CTRL_BYTES;
+    if (ipc_handle) {
+#if defined(ADSB_HOST_EMU)
+        memset(ipc_handle, 0, ADSB_IPC_HANDLE_BYTES);
+#else
+        static_assert(sizeof(cudaIpcMemHandle_t) == ADSB_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) return fail(ctx, ADSB_E_PEER, "cudaIpcGetMemHandle", e);
+        memcpy(ipc_handle, &h, sizeof(h));
+#endif
+    }
+    return ADSB_OK;
+}
+
+int adsb_shard_write(adsb_ctx *ctx, size_t byte_offset, const void *src, size_t bytes, void *stream)
+{
+    if (!ctx || !src) return ADSB_E_INVAL;
+    if (!ctx->shard.own_base || byte_offset + bytes > ctx->shard.own_bytes - ADSB_SHARD_CTRL_BYTES)
+        return fail(ctx, ADSB_E_INVAL, "adsb_shard_write: outside the allocation of adsb_shard_alloc");
+    ON_DEVICE(ctx);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    CK(cudaMemcpyAsync(static_cast<char *>(ctx->shard.own_base) + ADSB_SHARD_CTRL_BYTES + byte_offset, src, bytes,
+                       cudaMemcpyDefault, s));
+    if (!stream) CK(cudaStreamSynchronize(s));
+    return ADSB_OK;
+}
+
+int adsb_shard_detach(adsb_ctx *ctx)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    DeviceGuard guard(ctx->device);
+#if !defined(ADSB_HOST_EMU)
+    if (ctx->shard.exec) cudaGraphExecDestroy(ctx->shard.exec);
+    if (ctx->shard.graph) cudaGraphDestroy(ctx->shard.graph);
+    ctx->shard.exec = nullptr;
+    ctx->shard.graph = nullptr;
+    for (int r = 0; r < ctx->shard.world; r++)
+        if (ctx->shard.ipc_opened[r]) cudaIpcCloseMemHandle(ctx->shard.peer_base[r]);
+#endif
+    for (int r = 0; r < kMaxWorld; r++) {
+        ctx->shard.peer_base[r] = nullptr;
+        ctx->shard.ipc_opened[r] = false;
+    }
+    ctx->shard.world = 0;
+    return ADSB_OK;
+}
+
+int adsb_shard_attach_ptrs(adsb_ctx *ctx, int rank, int world, void *const *peer_bases)
+{
+    if (!ctx || !peer_bases || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return ADSB_E_INVAL;
+    adsb_shard_detach(ctx);
+    for (int r = 0; r < world; r++) {
+        if (!peer_bases[r]) return fail(ctx, ADSB_E_INVAL, "adsb_shard_attach_ptrs: null base pointer");
+        ctx->shard.peer_base[r] = peer_bases[r];
+    }
+    ctx->shard.rank = rank;
+    ctx->shard.world = world;
+    return ADSB_OK;
+}
+
+int adsb_shard_attach(adsb_ctx *ctx, int rank, int world, const void *ipc_handles)
+{
+    if (!ctx || !ipc_handles || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return ADSB_E_INVAL;
+    if (!ctx->shard.own_base) return fail(ctx, ADSB_E_INVAL, "adsb_shard_attach: call adsb_shard_alloc first");
+#if defined(ADSB_HOST_EMU)
+    return fail(ctx, ADSB_E_PEER, "no CUDA IPC in the host emulation");
+#else
+    ON_DEVICE(ctx);
+    adsb_shard_detach(ctx);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) {
+            ctx->shard.peer_base[r] = ctx->shard.own_base;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(ipc_handles) + (size_t)r * ADSB_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            ctx->shard.world = r;          // close what was opened so far
+            adsb_shard_detach(ctx);
+            return fail(ctx, ADSB_E_PEER, "cudaIpcOpenMemHandle (peer access between the GPUs needed)", e);
+        }
+        ctx->shard.peer_base[r] = p;
+        ctx->shard.ipc_opened[r] = true;
+    }
+    ctx->shard.rank = rank;
+    ctx->shard.world = world;
+    return ADSB_OK;
+#endif
+}
+
+namespace {
+
+// one step of shard `rank`, issued on stream s (phases: ADSB_SHARD_PH_*)
+int shard_issue(adsb_ctx *ctx, int fmt, size_t items, float threshold, int phases, cudaStream_t s)
+{
+    const int rank = ctx->shard.rank, world = ctx->shard.world;
+    const bool first = rank == 0, lastr = rank == world - 1;
+    auto ctrl_of = [&](int r) { return reinterpret_cast<ShardCtrl *>(ctx->shard.peer_base[r]); };
+    auto samples_of = [&](int r) { return static_cast<char *>(ctx->shard.peer_base[r]) + ADSB_SHARD_CTRL_BYTES; };
+    ShardCtrl *own = ctrl_of(rank);
+    ShardCtrl *left = first ? nullptr : ctrl_of(rank - 1), *right = lastr ? nullptr : ctrl_of(rank + 1);
+    // window of this shard: [left neighbour's shard | own samples | right neighbour's shard]; rank 0 has the
+    // 8*sps-1 zeros of GNU Radio's history instead of a left neighbour (whole-buffer semantics)
+    const long long L = (long long)items, h1 = ctx->hist;
+    const long long lead = first ? h1 : L;
+    const long long own_lo = first ? 0 : lead;
+    const long long own_hi = lead + L - (lastr ? h1 : 0);      // falls owned: [own_lo, own_hi)
+    const long long base = first ? 0 : (long long)rank * L + h1 - lead;
+    if (own_hi <= own_lo) return fail(ctx, ADSB_E_INVAL, "shard too small");
+    const long long n_tiles = tiles_for(ctx, own_hi, lead);
+    if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "too many tiles for this context");
+    int rc;
+    const bool ph_sig = phases & ADSB_SHARD_PH_SIGNAL, ph_scan = phases & ADSB_SHARD_PH_SCAN;
+    const bool ph_exp = phases & ADSB_SHARD_PH_EXPORT, ph_plan = phases & ADSB_SHARD_PH_PLAN, ph_check = phases & ADSB_SHARD_PH_CHECK;
+    if (ph_sig && !ph_scan && world > 1) {
+        ADSB_LAUNCH(shard_sync_kernel, 1, 1, 0, s, own, left, right, ctx->d_hdr, 1, 0);
+        CK(cudaGetLastError());
+    }
+    if (ph_scan) {
+        if ((rc = begin_call(ctx, n_tiles, own_hi - lead + 1, s))) return rc;
+        if (world > 1) {      // (signal and) wait in one launch, after the header reset: a timeout is reported through it
+            ADSB_LAUNCH(shard_sync_kernel, 1, 1, 0, s, own, left, right, ctx->d_hdr, ph_sig ? 1 : 0, 1);
+            CK(cudaGetLastError());
+        }
+        ScanParams P = make_params(ctx, samples_of(rank), (size_t)L, (size_t)lead, (size_t)own_hi, (size_t)own_lo, threshold,
+                                   base, /*prev_bit*/ first ? (0.0f >= threshold) : 0, 1);
+        if (!first) {
+            P.in_left = samples_of(rank - 1);
+            P.left_off = 0;                              // lead == L: window index i < lead is the neighbour's item i
+        }
+        if (!lastr) {
+            P.in_right = samples_of(rank + 1);
+            P.n_right = L;
+        }
+        P.win_hi = P.n_loc + P.n_right;
+        if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], s));
+        CK(launch_scan(ctx, P, fmt, 0u, (unsigned)n_tiles, s));
+        if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], s));
+        if ((rc = launch_resolve(ctx, n_tiles, base, -1, s))) return rc;
+        if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], s));
+        ctx->last.pending = true;
+        ctx->last.n_out = own_hi;
+        ctx->last.lead = lead;
+        ctx->last.base = base;
+        ctx->last.eob_in = -1;
+        ctx->last.left_is_start = 0;       // sharded mode never advances the carried framer state
+        ctx->last.stream = s;
+    }
+    if (world > 1) {
+        PeerCtrls pc;
+        memset(&pc, 0, sizeof(pc));
+        for (int r = 0; r < world; r++) pc.p[r] = ctrl_of(r);
+        const long long blank = 63LL * ctx->sps;
+        if ((ph_exp || ph_plan || ph_check) && !ctx->last.pending)
+            return fail(ctx, ADSB_E_INVAL, "adsb_shard_step: carry phase without a scan phase");
+        // round 0: export the latest resolve's summary to every rank / wait for everyone's and plan
+        if (ph_exp || ph_plan)
+            ADSB_LAUNCH(shard_carry_kernel, 1, kMaxWorld, 0, s, ctx->d_hdr, own, pc, world, rank, base, blank, 0, ph_exp ? 1 : 0,
+                        ph_plan ? 1 : 0);
+        if (ph_plan) {
+            if ((rc = zero_cand_totals(ctx, ctx->last.n_out - ctx->last.lead + 1, s))) return rc;
+            if ((rc = launch_resolve(ctx, n_tiles, base, 0, s, true, true))) return rc;    // no-ops unless carry_need
+        }
+        // round 1: the same exchange after the fix-ups, only to check that nothing is left to fix
+        if (ph_plan || ph_check)
+            ADSB_LAUNCH(shard_carry_kernel, 1, kMaxWorld, 0, s, ctx->d_hdr, own, pc, world, rank, base, blank, 1, ph_plan ? 1 : 0,
+                        ph_check ? 1 : 0);
+        CK(cudaGetLastError());
+    }
+    return ADSB_OK;
+}
+
+}  // namespace
+
+int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold, int phases, int use_graph, void *stream)
+{
+    if (!ctx || fmt < 0 || fmt >= kNumFmt || shard_items == 0 || !(phases & ADSB_SHARD_PH_ALL)) return ADSB_E_INVAL;
+    if (!ctx->shard.world) return fail(ctx, ADSB_E_INVAL, "adsb_shard_step: attach first");
+    if (shard_items > ctx->max_items) return fail(ctx, ADSB_E_INVAL, "shard_items exceeds max_items given to adsb_create");
+    if (shard_items < (size_t)(120 * ctx->sps + 256)) return fail(ctx, ADSB_E_INVAL, "shard shorter than a burst plus the noise window");
+    ON_DEVICE(ctx);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+#if !defined(ADSB_HOST_EMU)
+    if (use_graph && !ctx->profile && ctx->scan_configured[fmt]) {
+        auto &k = ctx->shard.key;
+        const bool same = ctx->shard.exec && k.fmt == fmt && k.phases == phases && k.items == shard_items &&
+                          k.thr == threshold && k.stream == s;
+        if (!same) {
+            if (ctx->shard.exec) cudaGraphExecDestroy(ctx->shard.exec);
+            if (ctx->shard.graph) cudaGraphDestroy(ctx->shard.graph);
+            ctx->shard.exec = nullptr;
+            ctx->shard.graph = nullptr;
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = shard_issue(ctx, fmt, shard_items, threshold, phases, s);
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(s, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return fail(ctx, ADSB_E_CUDA, "cudaStreamEndCapture", e);
+            ctx->shard.graph = g;
+            CK(cudaGraphInstantiate(&ctx->shard.exec, g, 0));
+            k.fmt = fmt;
+            k.phases = phases;
+            k.items = shard_items;
+            k.thr = threshold;
+            k.stream = s;
+        }
+        CK(cudaGraphLaunch(ctx->shard.exec, s));
+        ctx->shard.steps_graph++;
+        return ADSB_OK;
+    }
+#else
+    (void)use_graph;
+#endif
+    ctx->shard.steps_plain++;
+    return shard_issue(ctx, fmt, shard_items, threshold, phases, s);
+}
+
 int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits)
 {
     if (!ctx || !ctx->last.pending) return ADSB_E_INVAL;
@@ -722,7 +987,12 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
     CK(cudaStreamSynchronize(s));
     const Header &h = ctx->h_stage->hdr;
     int rc = status_of(ctx, h);
+    if (h.carry_unstable)       // per-call counter: hand it out once, then start the next call from zero
+        cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_hdr) + offsetof(Header, carry_unstable), 0, sizeof(unsigned), s);
     if (rc) {
+        // the call's tags are lost, but the stream position is not: prev_in0 must become x[n_out - 1] (framer.py:87)
+        if (ctx->last.left_is_start && !(h.flags & kFlagPeerTimeout))
+            ctx->prev_in0 = (ctx->last.n_out - 1 >= ctx->last.lead) ? h.x_last : 0.0f;
         ctx->last.pending = false;
         return rc;
     }

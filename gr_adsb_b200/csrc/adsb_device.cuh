@@ -68,8 +68,15 @@ struct Header {
 struct ScanParams {
     const void *in;        // float (|IQ|^2), float2 (IQ), short2 (sc16 IQ) or uchar2 (cu8 IQ)
     long long n_arr;       // items in `in`
-    long long lead;        // virtual zero items before in[0]; window index = array index + lead
+    long long lead;        // items before in[0]: zeros (stream start), or the left neighbour's shard when in_left is set;
+                           // window index = array index + lead
     long long n_loc;       // lead + n_arr
+    // multi-GPU peer mode (adsb_shard_step): the neighbouring shards, read in place over NVLink by the edge tiles
+    const void *in_left;   // window index i in [0, lead) is in_left[left_off + i] (null: zeros)
+    long long left_off;
+    const void *in_right;  // window index n_loc + j is in_right[j], j < n_right (null: zeros)
+    long long n_right;
+    long long win_hi;      // n_loc + n_right: end of the samples this call can see
     long long own_lo;      // falls owned: window index in [own_lo, own_hi)
     long long own_hi;
     long long base;        // added to window index in the emitted records
@@ -214,10 +221,11 @@ __device__ __forceinline__ float load_x(const void *in, long long j)
 template <int FMT>
 __device__ __forceinline__ float window_x(const ScanParams &P, long long i)
 {
-    long long j = i - P.lead;
-    if (j < 0 || j >= P.n_arr)
-        return 0.0f;
-    return load_x<FMT>(P.in, j);
+    const long long j = i - P.lead;
+    if (j >= 0 && j < P.n_arr) return load_x<FMT>(P.in, j);
+    if (j < 0) return (P.in_left && i >= 0) ? load_x<FMT>(P.in_left, P.left_off + i) : 0.0f;
+    const long long jr = j - P.n_arr;
+    return (P.in_right && jr < P.n_right) ? load_x<FMT>(P.in_right, jr) : 0.0f;
 }
 
 // total order on non-NaN floats as unsigned keys

@@ -264,6 +264,151 @@ __global__ void carry_plan_kernel(Header *h, const long long *gathered, int worl
     }
 }
 
+// ---- multi-GPU peer mode: neighbour hand-shake and blanking carry through peer-mapped control blocks ----------
+// Every rank owns one ShardCtrl in its symmetric allocation (adsb_shard_alloc); the other ranks write into it over
+// NVLink.  All waits are bounded (kPeerTimeoutNs) and report through Header.flags instead of hanging the GPU.
+constexpr int kMaxWorld = 32;
+constexpr unsigned kFlagPeerTimeout = 32u;
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ULL;
+
+struct ShardCtrl {
+    unsigned long long ready[2];      // step counter of the left [0] / right [1] neighbour, written by that neighbour
+    unsigned long long step;          // this rank's step counter
+    unsigned long long xchg;          // this rank's carry-exchange counter (one per round-0 export; stamps the slots)
+    unsigned long long pad[4];
+    long long slot[2][kMaxWorld][4];  // [round][rank] = first candidate, last hit, incoming state assumed, step stamp
+};
+static_assert(sizeof(ShardCtrl) <= 8192, "control block must fit ADSB_SHARD_CTRL_BYTES");
+
+struct PeerCtrls {
+    ShardCtrl *p[kMaxWorld];
+};
+
+__device__ __forceinline__ unsigned long long now_ns()
+{
+#if defined(ADSB_HOST_EMU)
+    static unsigned long long t = 0;
+    return t += 1000000ULL;            // every look at the clock is a millisecond: a wait that cannot succeed ends at once
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+__device__ __forceinline__ void fence_system()
+{
+#if !defined(ADSB_HOST_EMU)
+    __threadfence_system();
+#endif
+}
+__device__ __forceinline__ unsigned long long vload64(const unsigned long long *p)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+// wait until *p >= want (step counters only grow); false on timeout
+__device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want)
+{
+    if (vload64(p) >= want) return true;
+    const unsigned long long t0 = now_ns();
+    while (vload64(p) < want) {
+        if (now_ns() - t0 > kPeerTimeoutNs) return false;
+#if !defined(ADSB_HOST_EMU)
+        __nanosleep(100);
+#endif
+    }
+    return true;
+}
+
+// phase bit 0 (signal): bump the own step counter and tell both neighbours that this rank's samples of the step are
+// resident; phase bit 1 (wait): hold the stream until both neighbours have said the same, so that the scan kernel's
+// edge tiles may read their shards in place.  One thread.
+__global__ void shard_sync_kernel(ShardCtrl *own, ShardCtrl *left, ShardCtrl *right, Header *hdr, int do_signal, int do_wait)
+{
+    if (do_signal) {
+        const unsigned long long k = own->step + 1;
+        own->step = k;
+        fence_system();                 // the samples written earlier on this stream are visible before the flag is
+        if (left) *reinterpret_cast<volatile unsigned long long *>(&left->ready[1]) = k;
+        if (right) *reinterpret_cast<volatile unsigned long long *>(&right->ready[0]) = k;
+    }
+    if (do_wait) {
+        const unsigned long long k = own->step;
+        bool ok = true;
+        if (left) ok = wait_ge(&own->ready[0], k) && ok;
+        if (right) ok = wait_ge(&own->ready[1], k) && ok;
+        fence_system();
+        if (!ok) atomicOr(&hdr->flags, kFlagPeerTimeout);
+    }
+}
+
+// Blanking carry without NCCL and without the host.  export: this rank's (first candidate, last hit, incoming state its
+// latest resolve assumed) goes into slot[round][rank] of EVERY rank's control block, stamped with the step counter.
+// plan: wait until all `world` slots of the own block carry this step's stamp, then evaluate the same plan as
+// gr_adsb_b200/sharding.py:carry_plan.  round 0 arms the conditional re-resolve (chain + compact) that follows on the
+// stream; round 1 only checks that nothing is left to fix (Header.carry_unstable otherwise).
+__global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, ShardCtrl *own, const PeerCtrls peers, int world,
+                                                                 int rank, long long base, long long blank, int round,
+                                                                 int do_export, int do_plan)
+{
+    const int t = threadIdx.x;
+    // every rank runs the same sequence of exchanges, so the counters agree without being communicated
+    __shared__ unsigned long long s_k;
+    if (t == 0) {
+        unsigned long long x = own->xchg;
+        if (do_export && round == 0) own->xchg = ++x;
+        s_k = x;
+    }
+    __syncthreads();
+    const unsigned long long k = s_k;
+    if (do_export && t < world) {
+        long long *dst = peers.p[t]->slot[round][rank];
+        volatile long long *vd = dst;
+        vd[0] = h->first_cand >= 0 ? base + h->first_cand : kCarryNone;
+        vd[1] = h->last_accept >= 0 ? base + h->last_accept : kCarryNone;
+        vd[2] = h->carry_used;
+        fence_system();
+        vd[3] = (long long)k;
+    }
+    if (!do_plan) return;
+    __shared__ int s_bad;
+    if (t == 0) s_bad = 0;
+    __syncthreads();
+    if (t < world) {
+        if (!wait_ge(reinterpret_cast<const unsigned long long *>(&own->slot[round][t][3]), k)) s_bad = 1;
+        fence_system();
+    }
+    __syncthreads();
+    if (t != 0) return;
+    if (s_bad) {
+        atomicOr(&h->flags, kFlagPeerTimeout);
+        h->carry_need = 0;
+        return;
+    }
+    long long e = kCarryNone, my_e = kCarryNone;
+    int my_need = 0, any = 0;
+    for (int r = 0; r < world; r++) {
+        const volatile long long *sl = own->slot[round][r];
+        const long long first = sl[0], last = sl[1], used = sl[2];
+        const bool changed = e != used;
+        const long long mx = e > used ? e : used;
+        const bool need = changed && first != kCarryNone && first <= mx;
+        if (r == rank) {
+            my_e = e;
+            my_need = need;
+        }
+        any |= need;
+        if (last != kCarryNone) e = last + blank;
+    }
+    if (round == 1) {
+        if (any) h->carry_unstable += 1;
+        h->carry_need = 0;
+    } else {
+        h->carry_need = my_need;
+        h->carry_ein = my_e;
+        h->carry_used = my_e;       // where no re-run is needed the result is the same under either value
+    }
+}
+
 // ---- "Conservative" error correction (decoder.py:304-323, 738-763): one thread per hit -----------------------
 // A hit that was demodulated, fails the parity check and carries DF 17..19 gets its 25-bit residual
 // (decoder.compute_crc_2: the division stops one step early) looked up among the residuals of all 1-bit and

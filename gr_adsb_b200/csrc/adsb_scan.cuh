@@ -171,7 +171,7 @@ __device__ __forceinline__ bool demod_in_range(const ScanParams &P, long long p)
 {
     // demod.py:67,82 in window coordinates: tag not late, last sample p + 119*sps + sps/2 inside in0
     const long long last = p + 119LL * P.sps + (P.sps >> 1);
-    return (!P.left_is_start || p >= P.hist) && last <= P.n_loc - 1;
+    return (!P.left_is_start || p >= P.hist) && last <= P.win_hi - 1;
 }
 
 // window sample i through shared memory when staged, global memory otherwise
@@ -279,7 +279,10 @@ __device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, lo
                                                 const unsigned (&crc_t)[4], bool always_valid, Rec &rec)
 {
     int n = kNoise;                                   // framer.py:156-159
-    if (!always_valid && p < kNoise) n = (int)p;
+    if (!always_valid && p < kNoise) {
+        n = (int)p;                                   // window start: the noise window is cut short
+        if (!P.left_is_start && lane == 0) atomicOr(&P.hdr->flags, kFlagHalo);   // a shard cannot know what lies before its view
+    }
     float v[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -508,7 +511,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     } else {
         for (int k = wid * 32; k < S; k += NT) {
             const long long i = w0 + k + lane;
-            const float v = (i >= 0 && i < P.n_loc) ? window_x<FMT>(P, i) : 0.0f;
+            const float v = (i >= 0 && i < P.win_hi) ? window_x<FMT>(P, i) : 0.0f;
             bool bit = v >= thr;
             if (i < 0) bit = P.left_is_start ? (i == -1 && P.prev_bit) : false;
             sm.mag[k + lane] = v;

@@ -16,6 +16,34 @@ two tiny resolve kernels wherever the true incoming state reaches their first ca
 LEFT_HALO = 256
 
 
+# ---- peer mode (the product path on NVLink machines): adsb_shard_* in include/adsb_b200.h ------------------------
+# Nothing is copied between GPUs.  Every rank keeps exactly its own `shard_items` samples in a symmetric allocation
+# that the other ranks map through CUDA IPC; the scan kernel's edge tiles read the neighbours' samples in place and
+# the blanking carry travels through peer-written slots.  torch.distributed is only the plumbing that hands the
+# 64-byte IPC handles around once at set-up.
+def peer_attach(ctx, dist, rank, world, sample_bytes):
+    """Allocate this rank's symmetric shard, exchange the IPC handles over `dist` (any backend) and map the peers.
+    Returns the device pointer of the sample area."""
+    ptr, handle = ctx.shard_alloc(sample_bytes)
+    if world == 1:
+        ctx.shard_attach_ptrs(0, 1, [ptr])
+        return ptr
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    ctx.shard_attach(rank, world, handles)
+    return ptr
+
+
+def peer_window(rank, world, shard_items, sps):
+    """Geometry of adsb_shard_step (mirrors shard_issue in csrc/adsb_api.cu): the GLOBAL window indices [own_lo, own_hi)
+    of the pulse falls rank `rank` owns; global window index = stream index + 8*sps - 1."""
+    h1 = 8 * sps - 1
+    lo = 0 if rank == 0 else rank * shard_items + h1
+    hi = (rank + 1) * shard_items + (0 if rank == world - 1 else h1)
+    return lo, hi
+
+
+
 def shard_geometry(rank, world, shard_items, sps):
     """Arguments of adsb_burst_work_dev for shard `rank` holding `shard_items` of the stream."""
     h1 = 8 * sps - 1

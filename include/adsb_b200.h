@@ -45,7 +45,8 @@ enum {
     ADSB_E_CAPACITY = -4,  /* more hits than the caller's `cap`; n_hits holds the number required      */
     ADSB_E_NODEVICE = -5,  /* no CUDA device / not an sm_100 part                                     */
     ADSB_E_HALO = -6,      /* a pulse run crosses the left edge of a halo'd shard (multi-GPU only)    */
-    ADSB_E_INTERNAL = -7
+    ADSB_E_INTERNAL = -7,
+    ADSB_E_PEER = -8       /* multi-GPU peer mode: IPC mapping failed or a neighbouring rank never reached the step */
 };
 
 /* adsb_hit.flags */
@@ -171,6 +172,50 @@ int adsb_burst_export_carry_dev(adsb_ctx *ctx, int64_t used_global, int64_t *d_o
  * stream is idle: non-zero means more rounds were needed than were issued). */
 int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int world, int rank, int final_check,
                                void *stream);
+
+/* ---- Multi-GPU peer mode: one long stream cut into `world` equal contiguous shards, one per GPU/process --------------
+ * (target semantics = ONE framer.work()/demod.work() call over the whole stream, framer.py:72-182,
+ * demod.py:57-136.)  Nothing is copied between GPUs: every rank keeps its shard in a "symmetric" allocation that the
+ * other ranks map (CUDA IPC over NVLink / NVSwitch); the scan kernel's edge tiles read the neighbouring shards in
+ * place -- the 100-sample noise window and pulse-run look-back to the left (framer.py:95-113,156-159), preamble + 112
+ * bits to the right (demod.py:75-95) -- and the one sequential quantity, the blanking state prev_eob_idx
+ * (framer.py:121-123,165), travels as three int64 per rank written straight into every rank's control block.
+ * Neither the host nor NCCL takes part in a step; the whole step is one CUDA graph launch.
+ *
+ *   adsb_shard_alloc        allocate [control block | samples] on the context's device, return the sample pointer and
+ *                           (optionally) the 64-byte CUDA IPC handle to hand to the other ranks (any transport)
+ *   adsb_shard_attach       map every rank's allocation from its IPC handle (handles[world][64], own entry ignored)
+ *   adsb_shard_attach_ptrs  same with ready-made device pointers to the START of each rank's allocation (ranks that
+ *                           live in one process, or memory mapped by other means); pointers stay owned by the caller
+ *   adsb_shard_write        copy a step's samples into this rank's sample area (from pinned host memory: the ingest)
+ *   adsb_shard_step         one step over this rank's `shard_items` samples of format `fmt` (ADSB_FMT_*), asynchronous
+ *                           on `stream`; every rank calls it with the same arguments.  phases = ADSB_SHARD_PH_ALL runs
+ *                           the whole step; the individual bits exist so that a single process driving several ranks
+ *                           (tests) can interleave them, and EXPORT|PLAN|CHECK repeats the carry exchange when
+ *                           adsb_counters.carry_unstable reports that one round was not enough (cascade through
+ *                           several shards).  use_graph != 0 replays the step as a captured CUDA graph.
+ *   results                 adsb_burst_finish (counters, hits with global window indices); the carried framer state of
+ *                           the context is left alone.  Waits on other ranks are bounded: ADSB_E_PEER after 2 s.
+ * Limits: shard_items >= 120*sps + 256; a pulse run or noise window reaching past the START of the left neighbour's
+ * shard is reported as ADSB_E_HALO. */
+#define ADSB_SHARD_CTRL_BYTES 8192
+#define ADSB_IPC_HANDLE_BYTES 64
+#define ADSB_SHARD_MAX_WORLD 32
+#define ADSB_SHARD_PH_SIGNAL 1   /* tell the neighbours that this rank's samples of the step are resident          */
+#define ADSB_SHARD_PH_SCAN   2   /* wait for the neighbours, scan + resolve assuming no incoming blanking state      */
+#define ADSB_SHARD_PH_EXPORT 4   /* publish (first candidate, last hit, state assumed) to every rank                 */
+#define ADSB_SHARD_PH_PLAN   8   /* wait for every rank's, re-resolve if the true incoming state demands, re-publish */
+#define ADSB_SHARD_PH_CHECK  16  /* wait for every rank's, count the step as unstable if a fix-up is still needed     */
+#define ADSB_SHARD_PH_ALL    31
+int adsb_shard_alloc(adsb_ctx *ctx, size_t sample_bytes, void **d_samples, void *ipc_handle);
+int adsb_shard_attach(adsb_ctx *ctx, int rank, int world, const void *ipc_handles);
+int adsb_shard_attach_ptrs(adsb_ctx *ctx, int rank, int world, void *const *peer_bases);
+int adsb_shard_detach(adsb_ctx *ctx);
+/* Copy `bytes` from `src` (host or device memory, pinned host memory for a truly asynchronous copy) to byte_offset of
+ * this rank's sample area: the ingest of a step.  stream == NULL: the context's stream, synchronised before returning. */
+int adsb_shard_write(adsb_ctx *ctx, size_t byte_offset, const void *src, size_t bytes, void *stream);
+int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold, int phases, int use_graph,
+                    void *stream);
 
 /* Measurement hook for bench.py: when enabled, adsb_burst_work_dev records CUDA events on its launch
  * stream before the scan kernel, after it and after the resolve kernels; adsb_profile_last waits for

@@ -22,9 +22,10 @@ def pytest_configure(config):
 
 
 def _have_gpu():
+    """The product needs only the CUDA runtime (no torch): ask the library itself."""
     try:
-        import torch
-        return torch.cuda.is_available()
+        from gr_adsb_b200 import _native
+        return int(_native.lib().adsb_device_count()) > 0
     except Exception:
         return False
 
