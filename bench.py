@@ -489,12 +489,17 @@ def main():
     globals()["SPS"] = args.sps
     globals()["DENSITY"] = args.density
 
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import gr_adsb_b200 as g
     from gr_adsb_b200 import sharding, synth
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -742,7 +747,8 @@ def main():
             line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -876,8 +876,8 @@ int shard_issue(adsb_ctx *ctx, int fmt, size_t items, float threshold, int phase
     }
     if (ph_scan) {
         if ((rc = begin_call(ctx, n_tiles, own_hi - lead + 1, s))) return rc;
-        if (world > 1) {      // (signal and) wait in one launch, after the header reset: a timeout is reported through it
-            ADSB_LAUNCH(shard_sync_kernel, 1, 1, 0, s, own, left, right, ctx->d_hdr, ph_sig ? 1 : 0, 1);
+        if (world > 1 && ph_sig) {     // the wait for the neighbours' signals happens inside the scan kernel's edge tiles
+            ADSB_LAUNCH(shard_sync_kernel, 1, 1, 0, s, own, left, right, ctx->d_hdr, 1, 0);
             CK(cudaGetLastError());
         }
         ScanParams P = make_params(ctx, samples_of(rank), (size_t)L, (size_t)lead, (size_t)own_hi, (size_t)own_lo, threshold,
@@ -891,6 +891,7 @@ int shard_issue(adsb_ctx *ctx, int fmt, size_t items, float threshold, int phase
             P.n_right = L;
         }
         P.win_hi = P.n_loc + P.n_right;
+        if (world > 1) P.peer_ready = own->ready;     // ready[0], ready[1], step are consecutive (ShardCtrl)
         if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], s));
         CK(launch_scan(ctx, P, fmt, 0u, (unsigned)n_tiles, s));
         if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], s));

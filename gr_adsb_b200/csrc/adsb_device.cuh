@@ -77,6 +77,8 @@ struct ScanParams {
     const void *in_right;  // window index n_loc + j is in_right[j], j < n_right (null: zeros)
     long long n_right;
     long long win_hi;      // n_loc + n_right: end of the samples this call can see
+    const unsigned long long *peer_ready;  // this rank's ShardCtrl: [0] left / [1] right neighbour's step counter, [2] own;
+                                           // tiles that may touch a neighbour's samples wait until it has reached the step
     long long own_lo;      // falls owned: window index in [own_lo, own_hi)
     long long own_hi;
     long long base;        // added to window index in the emitted records
@@ -226,6 +228,44 @@ __device__ __forceinline__ float window_x(const ScanParams &P, long long i)
     if (j < 0) return (P.in_left && i >= 0) ? load_x<FMT>(P.in_left, P.left_off + i) : 0.0f;
     const long long jr = j - P.n_arr;
     return (P.in_right && jr < P.n_right) ? load_x<FMT>(P.in_right, jr) : 0.0f;
+}
+
+// ---- bounded waits on flags other GPUs write (multi-GPU peer mode) ---------------------------------------------
+constexpr unsigned kFlagPeerTimeout = 32u;
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ULL;
+__device__ __forceinline__ unsigned long long now_ns()
+{
+#if defined(ADSB_HOST_EMU)
+    static unsigned long long t = 0;
+    return t += 1000000ULL;            // every look at the clock is a millisecond: a wait that cannot succeed ends at once
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+__device__ __forceinline__ void fence_system()
+{
+#if !defined(ADSB_HOST_EMU)
+    __threadfence_system();
+#endif
+}
+__device__ __forceinline__ unsigned long long vload64(const unsigned long long *p)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+// wait until *p >= want (step counters only grow); false on timeout
+__device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want)
+{
+    if (vload64(p) >= want) return true;
+    const unsigned long long t0 = now_ns();
+    while (vload64(p) < want) {
+        if (now_ns() - t0 > kPeerTimeoutNs) return false;
+#if !defined(ADSB_HOST_EMU)
+        __nanosleep(100);
+#endif
+    }
+    return true;
 }
 
 // total order on non-NaN floats as unsigned keys

@@ -268,8 +268,6 @@ __global__ void carry_plan_kernel(Header *h, const long long *gathered, int worl
 // Every rank owns one ShardCtrl in its symmetric allocation (adsb_shard_alloc); the other ranks write into it over
 // NVLink.  All waits are bounded (kPeerTimeoutNs) and report through Header.flags instead of hanging the GPU.
 constexpr int kMaxWorld = 32;
-constexpr unsigned kFlagPeerTimeout = 32u;
-constexpr unsigned long long kPeerTimeoutNs = 2000000000ULL;
 
 struct ShardCtrl {
     unsigned long long ready[2];      // step counter of the left [0] / right [1] neighbour, written by that neighbour
@@ -284,44 +282,9 @@ struct PeerCtrls {
     ShardCtrl *p[kMaxWorld];
 };
 
-__device__ __forceinline__ unsigned long long now_ns()
-{
-#if defined(ADSB_HOST_EMU)
-    static unsigned long long t = 0;
-    return t += 1000000ULL;            // every look at the clock is a millisecond: a wait that cannot succeed ends at once
-#else
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-#endif
-}
-__device__ __forceinline__ void fence_system()
-{
-#if !defined(ADSB_HOST_EMU)
-    __threadfence_system();
-#endif
-}
-__device__ __forceinline__ unsigned long long vload64(const unsigned long long *p)
-{
-    return *reinterpret_cast<const volatile unsigned long long *>(p);
-}
-// wait until *p >= want (step counters only grow); false on timeout
-__device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want)
-{
-    if (vload64(p) >= want) return true;
-    const unsigned long long t0 = now_ns();
-    while (vload64(p) < want) {
-        if (now_ns() - t0 > kPeerTimeoutNs) return false;
-#if !defined(ADSB_HOST_EMU)
-        __nanosleep(100);
-#endif
-    }
-    return true;
-}
-
-// phase bit 0 (signal): bump the own step counter and tell both neighbours that this rank's samples of the step are
-// resident; phase bit 1 (wait): hold the stream until both neighbours have said the same, so that the scan kernel's
-// edge tiles may read their shards in place.  One thread.
+// signal: bump the own step counter and tell both neighbours that this rank's samples of the step are resident.
+// wait: hold the stream until both neighbours have said the same (the scan kernel's edge tiles do this wait
+// themselves -- wait_neighbours() in adsb_scan.cuh -- so the production step only launches the signal).  One thread.
 __global__ void shard_sync_kernel(ShardCtrl *own, ShardCtrl *left, ShardCtrl *right, Header *hdr, int do_signal, int do_wait)
 {
     if (do_signal) {

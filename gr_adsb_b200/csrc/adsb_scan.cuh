@@ -509,6 +509,19 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             }
         }
     } else {
+        if (P.peer_ready) {
+            // multi-GPU peer mode: this tile may read a neighbour's samples -- not before that rank has said they are
+            // resident for this step (its shard_sync_kernel writes the step counter into our control block)
+            if (tid == 0) {
+                const unsigned long long k = P.peer_ready[2];
+                bool ok = true;
+                if (P.in_left) ok = wait_ge(P.peer_ready + 0, k) && ok;
+                if (P.in_right) ok = wait_ge(P.peer_ready + 1, k) && ok;
+                fence_system();
+                if (!ok) atomicOr(&P.hdr->flags, kFlagPeerTimeout);
+            }
+            gb.sync();
+        }
         for (int k = wid * 32; k < S; k += NT) {
             const long long i = w0 + k + lane;
             const float v = (i >= 0 && i < P.win_hi) ? window_x<FMT>(P, i) : 0.0f;
