@@ -443,19 +443,42 @@ def block_api_leg(g, synth):
     x = synth.mag2(d["iq"])
     out = {"stream": "BASELINE configs[0]: 2 Msps float32 |IQ|^2, 100 bursts/s, %d samples, host buffers, lock-step scheduler" % n,
            "runs": []}
+    makers = {"framer+demod": lambda: [g.framer(2e6, THRESHOLD), g.demod(2e6)],
+              "framer+demod(batch)": lambda: [g.framer(2e6, THRESHOLD), g.demod(2e6, batch=True)],
+              "burst": lambda: [g.burst(2e6, THRESHOLD)],
+              "burst(batch)": lambda: [g.burst(2e6, THRESHOLD, batch=True)]}
     for chunk in (8192, 65536):
-        for kind in ("framer+demod", "burst"):
-            mk = (lambda: [g.framer(2e6, THRESHOLD), g.demod(2e6)]) if kind == "framer+demod" else (lambda: [g.burst(2e6, THRESHOLD)])
+        for kind, mk in makers.items():
             flowgraph.run_chain(mk(), x[: chunk * 8], chunk)            # warm up (contexts, kernels)
             blocks = mk()
             t0 = time.perf_counter()
             r = flowgraph.run_chain(blocks, x, chunk)
             dt = time.perf_counter() - t0
             calls = (n + chunk - 1) // chunk
-            out["runs"].append({"blocks": kind, "items_per_work": chunk, "us_per_work_call%s" % ("_pair" if kind != "burst" else ""):
-                                dt / calls * 1e6, "msamples_per_s": n / dt / 1e6, "tags": r["n_tags"], "pdus": r["n_pdus"]})
+            lat = [b._ctx.latency_stats() for b in blocks]
+            out["runs"].append({"blocks": kind, "items_per_work": chunk,
+                                "us_per_work_call%s" % ("_pair" if "+" in kind else ""): dt / calls * 1e6,
+                                "msamples_per_s": n / dt / 1e6, "tags": r["n_tags"], "pdus": r["n_pdus"],
+                                "messages": len(blocks[-1]._msgs["demodulated"]),
+                                "device_calls_on_latency_path": [a for a, _ in lat],
+                                "demod_bits_from_framer_pass": getattr(blocks[-1], "cache_hits", None)})
             for b in blocks:
                 b.close()
+    # the same stream at BASELINE configs[1] density (10k bursts/s): the per-burst Python (tags, PDUs) starts to count
+    d2 = synth.synth_numpy(1 << 20, sps=2, n_bursts=int((1 << 20) * 5e-3), seed=4)
+    x2 = synth.mag2(d2["iq"])
+    for kind in ("framer+demod", "burst", "burst(batch)"):
+        flowgraph.run_chain(makers[kind](), x2[: 8192 * 4], 8192)
+        blocks = makers[kind]()
+        t0 = time.perf_counter()
+        r = flowgraph.run_chain(blocks, x2, 8192)
+        dt = time.perf_counter() - t0
+        out["runs"].append({"blocks": kind, "items_per_work": 8192, "stream": "configs[1] density (10k bursts/s), 2^20 samples",
+                            "us_per_work_call%s" % ("_pair" if "+" in kind else ""): dt / ((1 << 20) // 8192) * 1e6,
+                            "msamples_per_s": (1 << 20) / dt / 1e6, "tags": r["n_tags"], "pdus": r["n_pdus"],
+                            "pdus_per_s": r["n_pdus"] / dt})
+        for b in blocks:
+            b.close()
     return out
 
 

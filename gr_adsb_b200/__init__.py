@@ -12,7 +12,7 @@ from ._native import (SHARD_PH_SIGNAL, SHARD_PH_SCAN, SHARD_PH_EXPORT, SHARD_PH_
 
 def __getattr__(name):
     # blocks import lazily: they need the native library, `synth` and the ABI constants do not
-    if name in ("framer", "demod", "burst"):
+    if name in ("framer", "demod", "burst", "pdu_unbatch", "split_batch", "feed_decoder"):
         from . import blocks
         return getattr(blocks, name)
     raise AttributeError(name)

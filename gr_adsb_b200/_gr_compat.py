@@ -62,11 +62,20 @@ if not HAVE_GNURADIO:
         def message_port_register_out(self, port):
             self._msgs.setdefault(port, [])
 
+        def message_port_register_in(self, port):
+            self._handlers = getattr(self, "_handlers", {})
+            self._handlers.setdefault(port, None)
+
+        def set_msg_handler(self, port, fn):
+            self._handlers = getattr(self, "_handlers", {})
+            self._handlers[port] = fn
+
         def message_port_pub(self, port, msg):
             self._msgs.setdefault(port, []).append(msg)
 
     class _Gr(object):
         sync_block = _SyncBlock
+        basic_block = _SyncBlock
         TPP_DONT, TPP_ALL_TO_ALL, TPP_ONE_TO_ONE = 0, 1, 2
 
     class _Pmt(object):

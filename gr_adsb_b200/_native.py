@@ -67,7 +67,7 @@ EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_creat
            "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
            "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev", "adsb_set_error_correction",
            "adsb_burst_mag_out", "adsb_shard_alloc", "adsb_shard_attach", "adsb_shard_attach_ptrs", "adsb_shard_detach",
-           "adsb_shard_write", "adsb_shard_step"]
+           "adsb_shard_write", "adsb_shard_step", "adsb_latency_stats", "adsb_set_latency_path", "adsb_latency_trace"]
 
 
 def lib():
@@ -140,6 +140,12 @@ def lib():
     L.adsb_shard_write.argtypes = [vp, sz, vp, sz, vp]
     L.adsb_shard_step.restype = i32
     L.adsb_shard_step.argtypes = [vp, i32, sz, f32, i32, i32, vp]
+    L.adsb_latency_stats.restype = i32
+    L.adsb_latency_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.adsb_latency_trace.restype = i32
+    L.adsb_latency_trace.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    L.adsb_set_latency_path.restype = i32
+    L.adsb_set_latency_path.argtypes = [vp, i32]
     L.adsb_profile_enable.restype = i32
     L.adsb_profile_enable.argtypes = [vp, i32]
     L.adsb_profile_last.restype = i32
@@ -256,6 +262,15 @@ class Context(object):
                                           float(np.float32(threshold)), int(base), _ptr(hits), cap, C.byref(n)))
         return hits[:n.value]
 
+    def burst_work_raw(self, host_ptr, fmt, n_in, lead, n_out, thr32, hits_ptr, cap, n_ref):
+        """The bare call for per-work() use (blocks.py): everything pre-converted by the caller -- host pointer (int),
+        threshold already rounded to float32, pointer / capacity of a reusable adsb_hit array, a ctypes size_t to
+        receive the count.  Returns the number of hits."""
+        rc = lib().adsb_burst_work(self._h, host_ptr, fmt, n_in, lead, n_out, thr32, 0, hits_ptr, cap, n_ref)
+        if rc != ADSB_OK:
+            self._check(rc)
+        return n_ref._obj.value
+
     def burst_work_ptr(self, host_ptr, c64, n_in, n_out, lead, threshold, base, hits):
         """Same, raw host pointer + caller-owned hits array (bench.py's end-to-end leg)."""
         n = C.c_size_t(0)
@@ -333,6 +348,15 @@ class Context(object):
     def shard_step(self, fmt, shard_items, threshold, phases=SHARD_PH_ALL, use_graph=False, stream=0):
         self._check(lib().adsb_shard_step(self._h, int(fmt), int(shard_items), float(np.float32(threshold)), int(phases),
                                           1 if use_graph else 0, C.c_void_p(stream)))
+
+    def latency_stats(self):
+        """(calls served by the one-kernel latency path, how many of them fell back to the resolve kernels)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(lib().adsb_latency_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_latency_path(self, on):
+        self._check(lib().adsb_set_latency_path(self._h, 1 if on else 0))
 
     # --- measurement hook ------------------------------------------------------------------------------
     def profile_enable(self, on=True):

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -11,6 +12,7 @@
 #include "adsb_device.cuh"
 #include "adsb_resolve.cuh"
 #include "adsb_scan.cuh"
+#include "adsb_small.cuh"
 
 using namespace adsb;
 
@@ -104,6 +106,9 @@ struct adsb_ctx {
     size_t d_mag_cap;
     int staged_fmt;              // format / item count of the input adsb_burst_work staged last (-1: none)
     size_t staged_n;
+    bool small_configured[2];    // latency-path kernel attributes set (float32 / complex64 input)
+    int small_fmt;
+    int no_small;                // ADSB_NO_LATENCY_PATH=1 in the environment: always take the throughput pipeline (A/B, debugging)
     bool scan_configured[kNumFmt];  // per sample format: shared-memory attributes of the scan kernel set on this device
     // multi-GPU peer mode (adsb_shard_*): symmetric allocation [ShardCtrl | samples] of every rank, mapped here
     struct {
@@ -124,6 +129,24 @@ struct adsb_ctx {
         } key;                   // what `exec` was captured for
         unsigned long long steps_graph, steps_plain;
     } shard;
+    // latency path (adsb_small.cuh): pinned, device-mapped staging of one small call
+    struct {
+        SmallOut *out;           // results + completion stamp
+        void *in;                // the call's samples
+        size_t in_bytes;
+        float *mag;              // |IQ|^2 of the call's samples (complex input), n_in items
+        size_t mag_items;
+        long long *sob;          // demod: tag positions / results
+        unsigned char *bits, *valid;
+        size_t tag_cap;
+        unsigned *d_done;        // device counter of small_demod_kernel
+        unsigned long long seq;
+        bool clean;              // the device header is as init_header_kernel leaves it
+        bool last_was_small;     // adsb_burst_mag_out: the latest input sits in `in`, its |IQ|^2 in `mag`
+        bool use_device_hits;    // the latest small call fell back to the resolve kernels: hits are in d_hits
+        unsigned long long calls, fallbacks;
+        double host_t[3];        // seconds: entry -> staged, -> launched, -> stamp seen (latest call)
+    } small;
     Rec *h_tmp;                  // host scratch of the two-block entry points
     size_t h_tmp_cap;
     unsigned char *h_bits;
@@ -399,6 +422,8 @@ int zero_cand_totals(adsb_ctx *ctx, long long n_out, cudaStream_t s)
 
 int begin_call(adsb_ctx *ctx, long long n_tiles, long long n_out, cudaStream_t s)
 {
+    ctx->small.clean = false;               // a throughput-path call dirties the header (small_call sets it again itself)
+    ctx->small.last_was_small = false;
     ADSB_LAUNCH(init_header_kernel, 1, 1, 0, s, ctx->d_hdr);
     CK(cudaGetLastError());
     size_t n = (size_t)(n_tiles / kTilesPerChunk) + 2;
@@ -440,6 +465,208 @@ int status_of(adsb_ctx *ctx, const Header &h)
     if (h.flags & kFlagPeerTimeout) return fail(ctx, ADSB_E_PEER, "a neighbouring rank did not reach the step (peer wait timed out)");
     if (h.flags & kFlagHalo) return fail(ctx, ADSB_E_HALO, "pulse run crosses the left halo edge");
     if (h.flags & (kFlagCandOverflow | kFlagHitOverflow)) return fail(ctx, ADSB_E_NOMEM, "candidate capacity exceeded (raise max_items)");
+    return ADSB_OK;
+}
+
+
+// ---- latency path ------------------------------------------------------------------------------------------
+double host_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+template <int SPS, int FMT>
+cudaError_t launch_small_t(const ScanParams &P, const SmallParams &Q, cudaStream_t s, bool *configured)
+{
+    const size_t smem = tile_smem_bytes(Geo<SPS, kThreads>::T, P.rh, kWarps);
+    if (!*configured) {
+        cudaError_t e = cudaFuncSetAttribute(small_work_kernel<SPS, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        *configured = true;
+    }
+    ADSB_LAUNCH((small_work_kernel<SPS, FMT>), (unsigned)Q.n_tiles, kThreads, smem, s, P, Q);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_small(adsb_ctx *c, const ScanParams &P, const SmallParams &Q, int fmt, cudaStream_t s)
+{
+    bool *cf = &c->small_configured[fmt == kFmtC64 ? 1 : 0];
+    if (fmt == kFmtC64) {
+        switch (c->sps) {
+        case 2: return launch_small_t<2, kFmtC64>(P, Q, s, cf);
+        case 4: return launch_small_t<4, kFmtC64>(P, Q, s, cf);
+        case 8: return launch_small_t<8, kFmtC64>(P, Q, s, cf);
+        default: return launch_small_t<0, kFmtC64>(P, Q, s, cf);
+        }
+    }
+    switch (c->sps) {
+    case 2: return launch_small_t<2, kFmtF32>(P, Q, s, cf);
+    case 4: return launch_small_t<4, kFmtF32>(P, Q, s, cf);
+    case 8: return launch_small_t<8, kFmtF32>(P, Q, s, cf);
+    default: return launch_small_t<0, kFmtF32>(P, Q, s, cf);
+    }
+}
+
+template <class T>
+int pinned_grow(adsb_ctx *ctx, T **p, size_t *have, size_t want_items, const char *what)
+{
+    if (*have >= want_items) return ADSB_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaHostAlloc((void **)p, want_items * sizeof(T), cudaHostAllocMapped);
+    if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, what, e);
+    *have = want_items;
+    return ADSB_OK;
+}
+
+// spin on a completion stamp the kernel writes into pinned host memory (no cudaStreamSynchronize on this path); the
+// stream is polled now and then so that a failed launch ends the wait
+int wait_stamp(adsb_ctx *ctx, const unsigned long long *stamp, unsigned long long seq, cudaStream_t s)
+{
+    const volatile unsigned long long *v = stamp;
+    for (unsigned long long spins = 0;; spins++) {
+        if (*v == seq) return ADSB_OK;
+        if ((spins & 0x3fff) == 0x3fff) {
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaSuccess) return (*v == seq) ? ADSB_OK : fail(ctx, ADSB_E_INTERNAL, "latency path: kernel ended without its completion stamp");
+            if (q != cudaErrorNotReady) return fail(ctx, ADSB_E_CUDA, "latency path kernel", q);
+        }
+    }
+}
+
+bool small_eligible(const adsb_ctx *ctx, int fmt, size_t n_in, size_t lead, size_t n_out)
+{
+    if (ctx->fec_mode != ADSB_FEC_NONE || ctx->profile || ctx->no_small) return false;
+    if (fmt != kFmtF32 && fmt != kFmtC64) return false;
+    return tiles_for(ctx, (long long)n_out, (long long)lead) <= kSmallTiles && tiles_for(ctx, (long long)n_out, (long long)lead) >= 1 &&
+           n_in <= (size_t)kSmallTiles * ctx->T + ctx->rh + ctx->hist;
+}
+
+// One work() call on the latency path.  Same results and state updates as the throughput path (adsb_burst_work ->
+// adsb_burst_finish); hits land in ctx->small.out->hits.
+int small_call(adsb_ctx *ctx, const void *in, int fmt, size_t n_in, size_t lead, size_t n_out, float threshold, long long base,
+               int do_demod, size_t *n_hits)
+{
+    int rc;
+    const size_t isz = fmt == kFmtC64 ? 8 : 4;
+    cudaStream_t s = ctx->stream;
+    if (!ctx->small.out) {
+        cudaError_t e = cudaHostAlloc((void **)&ctx->small.out, sizeof(SmallOut), cudaHostAllocMapped);
+        if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, "pinned result block", e);
+        memset(ctx->small.out, 0, sizeof(SmallOut));
+    }
+    {
+        size_t have = ctx->small.in_bytes;
+        unsigned char *p = static_cast<unsigned char *>(ctx->small.in);
+        if ((rc = pinned_grow(ctx, &p, &have, ((size_t)kSmallTiles * ctx->T + ctx->rh + ctx->hist + 64) * 8, "pinned input staging"))) return rc;
+        ctx->small.in = p;
+        ctx->small.in_bytes = have;
+    }
+    const bool want_mag = fmt == kFmtC64;
+    if (want_mag && (rc = pinned_grow(ctx, &ctx->small.mag, &ctx->small.mag_items, (size_t)kSmallTiles * ctx->T + ctx->rh + ctx->hist + 64,
+                                      "pinned |IQ|^2 staging")))
+        return rc;
+    const long long n_tiles = tiles_for(ctx, (long long)n_out, (long long)lead);
+    if (!ctx->small.clean) {        // a throughput-path call came in between: one header reset puts the device back in step
+        if ((rc = begin_call(ctx, n_tiles, (long long)n_out, s))) return rc;
+        ctx->small.clean = true;
+    }
+    const double th0 = host_now();
+    memcpy(ctx->small.in, in, n_in * isz);      // GNU Radio's buffers are pageable: stage through pinned memory
+    const double th1 = host_now();
+    const int prev_bit = (lead != 0) ? (0.0f >= threshold) : (ctx->prev_in0 >= threshold);
+    const long long eob_in = ctx->prev_eob;
+    // up to 128 KiB the kernel reads the pinned staging buffer in place (one PCIe round trip, no copy call); beyond that
+    // the copy engine moves it at twice the bandwidth zero-copy reads reach and the kernel reads device memory
+    const void *src = ctx->small.in;
+    if (n_in * isz > (128u << 10)) {
+        if ((rc = ensure_input(ctx, n_in * isz))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_in, ctx->small.in, n_in * isz, cudaMemcpyHostToDevice, s));
+        src = ctx->d_in;
+    }
+    ScanParams P = make_params(ctx, src, n_in, lead, n_out, 0, threshold, base, prev_bit, do_demod);
+    P.prefetch_tiles = 0;
+    SmallParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.out = ctx->small.out;
+    Q.seq = ++ctx->small.seq;
+    Q.eob_in = eob_in;
+    Q.blank = 63 * ctx->sps;
+    Q.n_tiles = (int)n_tiles;
+    if (want_mag) {
+        Q.mag_out = ctx->small.mag;
+        Q.mag_first = (long long)lead;          // window index of in[0]
+        Q.mag_n = (long long)n_in;
+    }
+    CK(launch_small(ctx, P, Q, fmt, s));
+    const double th2 = host_now();
+    ctx->small.calls++;
+    if ((rc = wait_stamp(ctx, &ctx->small.out->seq, Q.seq, s))) {
+        ctx->small.clean = false;
+        return rc;
+    }
+    ctx->small.host_t[0] = th1 - th0;
+    ctx->small.host_t[1] = th2 - th1;
+    ctx->small.host_t[2] = host_now() - th2;
+    ctx->staged_fmt = -1;
+    ctx->small.last_was_small = true;
+    ctx->staged_n = n_in;
+    ctx->small_fmt = fmt;
+    ctx->last.pending = true;
+    ctx->last.n_out = (long long)n_out;
+    ctx->last.lead = (long long)lead;
+    ctx->last.base = base;
+    ctx->last.eob_in = eob_in;
+    ctx->last.left_is_start = 1;
+    ctx->last.stream = s;
+    Header h = ctx->small.out->hdr;
+    if (h.flags & kFlagSmallOverflow) {
+        // more candidates than the in-kernel resolve holds: the resolve kernels finish the call from the same records
+        ctx->small.fallbacks++;
+        ctx->small.clean = false;
+        ctx->small.use_device_hits = true;
+        if ((rc = zero_cand_totals(ctx, (long long)n_out, s))) return rc;
+        if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
+        return adsb_burst_finish(ctx, nullptr, nullptr, 0, n_hits);
+    }
+    ctx->small.use_device_hits = false;
+    ctx->last.pending = false;
+    rc = status_of(ctx, h);
+    if (rc) {
+        ctx->prev_in0 = ((long long)n_out - 1 >= (long long)lead) ? h.x_last : 0.0f;
+        return rc;
+    }
+    adsb_counters &c = ctx->counters;
+    c.n_samples = (uint64_t)n_out;
+    c.n_candidates = h.n_cand;
+    c.n_hits = h.n_hits;
+    c.n_demod = h.n_demod;
+    c.n_crc_ok = h.n_crc;
+    c.last_pulse = h.last_pulse;
+    c.last_accept = h.last_accept;
+    c.first_candidate = h.first_cand;
+    c.carry_unstable = 0;
+    c.n_fec_fixed = 0;
+    c.any_rise = (h.flags & kFlagRise) ? 1u : 0u;
+    c.any_fall = (h.flags & kFlagFall) ? 1u : 0u;
+    ctx->prev_eob = next_eob(h, eob_in, (long long)n_out, ctx->sps);      // framer.py:121-123,165,177-179
+    ctx->prev_in0 = ((long long)n_out - 1 >= (long long)lead) ? h.x_last : 0.0f;   // framer.py:87
+    *n_hits = (size_t)h.n_hits;
+    return ADSB_OK;
+}
+
+// where the hit records of the latest small_call are (pinned result block, or the device after a fallback)
+int small_fetch_hits(adsb_ctx *ctx, Rec *dst, size_t n)
+{
+    if (!n) return ADSB_OK;
+    if (!ctx->small.use_device_hits) {
+        memcpy(dst, ctx->small.out->hits, n * sizeof(Rec));
+        return ADSB_OK;
+    }
+    CK(cudaMemcpy(dst, ctx->d_hits, n * sizeof(Rec), cudaMemcpyDeviceToHost));
     return ADSB_OK;
 }
 
@@ -499,6 +726,13 @@ void adsb_destroy(adsb_ctx *ctx)
     cudaFree(ctx->d_valid);
     cudaFree(ctx->d_mag);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->small.out) cudaFreeHost(ctx->small.out);
+    if (ctx->small.in) cudaFreeHost(ctx->small.in);
+    if (ctx->small.mag) cudaFreeHost(ctx->small.mag);
+    if (ctx->small.sob) cudaFreeHost(ctx->small.sob);
+    if (ctx->small.bits) cudaFreeHost(ctx->small.bits);
+    if (ctx->small.valid) cudaFreeHost(ctx->small.valid);
+    cudaFree(ctx->small.d_done);
     free(ctx->h_tmp);
     free(ctx->h_bits);
     for (int i = 0; i < kEvRing; i++)
@@ -541,6 +775,11 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
         ctx->prefetch_tiles = e ? (unsigned)atoi(e) : (unsigned)(ctx->num_sms * 2);
     }
     ctx->err[0] = 0;
+    ctx->small.clean = false;
+    {
+        const char *e = getenv("ADSB_NO_LATENCY_PATH");
+        ctx->no_small = (e && e[0] == '1') ? 1 : 0;
+    }
 
     auto die = [&](int code, const char *what, cudaError_t e) {
         char msg[256];
@@ -641,6 +880,30 @@ int adsb_get_counters(const adsb_ctx *ctx, adsb_counters *out)
 {
     if (!ctx || !out) return ADSB_E_INVAL;
     *out = ctx->counters;
+    return ADSB_OK;
+}
+
+int adsb_latency_stats(const adsb_ctx *ctx, uint64_t *calls, uint64_t *fallbacks)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    if (calls) *calls = ctx->small.calls;
+    if (fallbacks) *fallbacks = ctx->small.fallbacks;
+    return ADSB_OK;
+}
+
+/* A/B builds (-DADSB_SMALL_TIMING=1): device timestamps of the latest latency-path call + host timestamps around it */
+int adsb_latency_trace(const adsb_ctx *ctx, uint64_t *dev8, double *host3)
+{
+    if (!ctx || !ctx->small.out) return ADSB_E_INVAL;
+    if (dev8) memcpy(dev8, ctx->small.out->t, sizeof(ctx->small.out->t));
+    if (host3) memcpy(host3, ctx->small.host_t, sizeof(ctx->small.host_t));
+    return ADSB_OK;
+}
+
+int adsb_set_latency_path(adsb_ctx *ctx, int on)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    ctx->no_small = on ? 0 : 1;
     return ADSB_OK;
 }
 
@@ -1035,6 +1298,17 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
     int rc = check_geometry(ctx, n_in, lead, n_out, 0);
     if (rc) return rc;
     ON_DEVICE(ctx);
+    if (small_eligible(ctx, is_c64, n_in, lead, n_out)) {
+        // GNU-Radio-sized call: one kernel launch, no copy calls (adsb_small.cuh)
+        size_t n = 0;
+        if ((rc = small_call(ctx, in, is_c64, n_in, lead, n_out, threshold, base, 1, &n))) return rc;
+        if (n_hits) *n_hits = n;
+        if (hits) {
+            if (n > cap) return fail(ctx, ADSB_E_CAPACITY, "hit capacity too small");
+            if ((rc = small_fetch_hits(ctx, reinterpret_cast<Rec *>(hits), n))) return rc;
+        }
+        return ADSB_OK;
+    }
     const size_t isz = (is_c64 == kFmtC64) ? 8 : (is_c64 == kFmtCU8) ? 2 : 4;
     ctx->staged_fmt = -1;
     if ((rc = ensure_input(ctx, n_in * isz))) return rc;
@@ -1083,6 +1357,12 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
 int adsb_burst_mag_out(adsb_ctx *ctx, float *out, size_t n_out)
 {
     if (!ctx || !out) return ADSB_E_INVAL;
+    if (ctx->small.last_was_small && n_out && n_out <= ctx->staged_n) {
+        // latency path: the kernel left |IQ|^2 of the call's samples in pinned memory (float32 input: the samples themselves)
+        const float *src = ctx->small_fmt == kFmtC64 ? ctx->small.mag : static_cast<const float *>(ctx->small.in);
+        memcpy(out, src + (ctx->staged_n - n_out), n_out * sizeof(float));
+        return ADSB_OK;
+    }
     if (ctx->staged_fmt < 0 || n_out == 0 || n_out > ctx->staged_n)
         return fail(ctx, ADSB_E_INVAL, "adsb_burst_mag_out: needs a preceding adsb_burst_work with n_in >= n_out");
     ON_DEVICE(ctx);
@@ -1120,6 +1400,24 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
     int rc = check_geometry(ctx, n_in, 0, n_out, 0);
     if (rc) return rc;
     ON_DEVICE(ctx);
+    if (small_eligible(ctx, kFmtF32, n_in, 0, n_out)) {
+        size_t n = 0;
+        if ((rc = small_call(ctx, in0, kFmtF32, n_in, 0, n_out, threshold, 0, 0, &n))) return rc;
+        *n_hits = n;
+        if (n > cap || (n && (!hit_idx || !hit_snr))) return fail(ctx, ADSB_E_CAPACITY, "hit capacity too small");
+        if (ctx->h_tmp_cap < n) {
+            free(ctx->h_tmp);
+            ctx->h_tmp = (Rec *)malloc((n + 64) * sizeof(Rec));
+            ctx->h_tmp_cap = ctx->h_tmp ? n + 64 : 0;
+            if (!ctx->h_tmp) return fail(ctx, ADSB_E_NOMEM, "malloc(hit scratch)");
+        }
+        if ((rc = small_fetch_hits(ctx, ctx->h_tmp, n))) return rc;
+        for (size_t i = 0; i < n; i++) {
+            hit_idx[i] = ctx->h_tmp[i].idx;
+            hit_snr[i] = ctx->h_tmp[i].snr;
+        }
+        return ADSB_OK;
+    }
     if ((rc = ensure_input(ctx, n_in * 4))) return rc;
     ctx->staged_fmt = -1;
     cudaStream_t s = ctx->stream;
@@ -1172,8 +1470,65 @@ int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *so
     if (n > ctx->max_items + (size_t)ctx->hist) return fail(ctx, ADSB_E_INVAL, "n exceeds max_items");
     ON_DEVICE(ctx);
     int rc;
+    {
+        // latency path: only the span the tags touch travels, through pinned memory the kernel reads and writes in place
+        long long lo = (long long)n, hi = 0;
+        for (size_t t = 0; t < n_tags; t++) {
+            const long long a = sob_idx[t], b = sob_idx[t] + 112LL * ctx->sps;
+            if (a < lo) lo = a;
+            if (b > hi) hi = b;
+        }
+        if (lo < 0) lo = 0;
+        if (hi > (long long)n) hi = (long long)n;
+        const size_t span = hi > lo ? (size_t)(hi - lo) : 0;
+        const size_t ring = ((size_t)kSmallTiles * ctx->T + ctx->rh + ctx->hist + 64) * 2;     // floats in the staging buffer
+        if (!ctx->no_small && n_tags <= 1024 && span <= ring) {
+            cudaStream_t s = ctx->stream;
+            unsigned char *p = static_cast<unsigned char *>(ctx->small.in);
+            size_t have = ctx->small.in_bytes;
+            if ((rc = pinned_grow(ctx, &p, &have, ring * 4, "pinned input staging"))) return rc;
+            ctx->small.in = p;
+            ctx->small.in_bytes = have;
+            if (!ctx->small.out) {
+                cudaError_t e = cudaHostAlloc((void **)&ctx->small.out, sizeof(SmallOut), cudaHostAllocMapped);
+                if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, "pinned result block", e);
+                memset(ctx->small.out, 0, sizeof(SmallOut));
+            }
+            if (ctx->small.tag_cap < n_tags) {
+                size_t c1 = ctx->small.tag_cap, c2 = ctx->small.tag_cap, c3 = ctx->small.tag_cap;
+                const size_t want = n_tags < 64 ? 64 : n_tags;
+                if ((rc = pinned_grow(ctx, &ctx->small.sob, &c1, want, "pinned tag staging"))) return rc;
+                c2 *= kMsgBits;
+                if ((rc = pinned_grow(ctx, &ctx->small.bits, &c2, want * kMsgBits, "pinned bit staging"))) return rc;
+                if ((rc = pinned_grow(ctx, &ctx->small.valid, &c3, want, "pinned tag staging"))) return rc;
+                ctx->small.tag_cap = want;
+            }
+            if (!ctx->small.d_done) {
+                CK(cudaMalloc((void **)&ctx->small.d_done, sizeof(unsigned)));
+                CK(cudaMemset(ctx->small.d_done, 0, sizeof(unsigned)));
+            }
+            if (span) memcpy(ctx->small.in, in0 + lo, span * sizeof(float));
+            memcpy(ctx->small.sob, sob_idx, n_tags * sizeof(long long));
+            ctx->small.last_was_small = false;
+            ctx->staged_fmt = -1;
+            unsigned blocks = (unsigned)((n_tags + kWarps - 1) / kWarps);
+            if (blocks > 64u) blocks = 64u;
+            const unsigned long long seq = ++ctx->small.seq;
+            ADSB_LAUNCH(small_demod_kernel, blocks, kThreads, 0, s, static_cast<const float *>(ctx->small.in), lo, (long long)n,
+                        ctx->small.sob, (int)n_tags, ctx->sps, ctx->small.bits, ctx->small.valid, &ctx->small.out->seq, seq,
+                        ctx->small.d_done);
+            CK(cudaGetLastError());
+            if ((rc = wait_stamp(ctx, &ctx->small.out->seq, seq, s))) return rc;
+            for (size_t t = 0; t < n_tags; t++) {
+                valid[t] = ctx->small.valid[t];
+                if (valid[t]) memcpy(bits + t * kMsgBits, ctx->small.bits + t * kMsgBits, kMsgBits);   // straddlers' bits stay untouched
+            }
+            return ADSB_OK;
+        }
+    }
     if ((rc = ensure_input(ctx, n * 4))) return rc;
     ctx->staged_fmt = -1;
+    ctx->small.last_was_small = false;
     if (n_tags > ctx->tag_cap) {
         cudaFree(ctx->d_sob);
         cudaFree(ctx->d_bits);

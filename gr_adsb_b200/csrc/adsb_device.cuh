@@ -54,7 +54,8 @@ struct Header {
     long long last_accept;           // max accepted centre, window coordinates (-1: none)
     unsigned flags;
     unsigned n_fec;                  // hits repaired by the conservative error correction
-    unsigned pad0[2];
+    unsigned tiles_done;             // latency path: tiles finished so far (the last one resolves the call)
+    unsigned pad0;
     float x_last;                    // x[n_out-1]  -> framer.py:87 prev_in0
     unsigned pad;
     long long first_cand;            // first candidate centre, window coordinates (-1: none)
@@ -217,6 +218,44 @@ __device__ __forceinline__ float load_x(const void *in, long long j)
     if (FMT == kFmtSC16) return mag2_sc16(ldg_stream_b32(reinterpret_cast<const unsigned *>(in) + j));
     if (FMT == kFmtCU8) return mag2_cu8(ldg_stream_b16(reinterpret_cast<const unsigned short *>(in) + j));
     return ldg_stream_f1(reinterpret_cast<const float *>(in) + j);
+}
+
+// raw bits of item j / their |IQ|^2: split so that a batch of loads can be issued before the first conversion waits for one
+template <int FMT>
+__device__ __forceinline__ unsigned long long load_raw(const void *in, long long j)
+{
+    if (FMT == kFmtC64) return ldg_stream_b64(reinterpret_cast<const float2 *>(in) + j);
+    if (FMT == kFmtSC16) return ldg_stream_b32(reinterpret_cast<const unsigned *>(in) + j);
+    if (FMT == kFmtCU8) return ldg_stream_b16(reinterpret_cast<const unsigned short *>(in) + j);
+    return ldg_stream_b32(reinterpret_cast<const unsigned *>(in) + j);
+}
+template <int FMT>
+__device__ __forceinline__ float raw_to_x(unsigned long long r)
+{
+    if (FMT == kFmtC64) return mag2_packed(r);
+    if (FMT == kFmtSC16) return mag2_sc16((unsigned)r);
+    if (FMT == kFmtCU8) return mag2_cu8((unsigned)r);
+    return __uint_as_float((unsigned)r);
+}
+
+// where window sample i lives: the array, a neighbouring shard, or nowhere (zeros); returns false for "nowhere"
+template <int FMT>
+__device__ __forceinline__ bool window_raw(const ScanParams &P, long long i, unsigned long long &raw)
+{
+    const long long j = i - P.lead;
+    if (j >= 0 && j < P.n_arr) {
+        raw = load_raw<FMT>(P.in, j);
+        return true;
+    }
+    if (j < 0) {
+        if (!(P.in_left && i >= 0)) return false;
+        raw = load_raw<FMT>(P.in_left, P.left_off + i);
+        return true;
+    }
+    const long long jr = j - P.n_arr;
+    if (!(P.in_right && jr < P.n_right)) return false;
+    raw = load_raw<FMT>(P.in_right, jr);
+    return true;
 }
 
 // window sample i (any i): zeros outside the array / inside the virtual lead

@@ -398,7 +398,9 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
 
 // ---- phases 1 + 2 of one tile, by the 256 scan threads (threads 0..255 of the CTA) --------------------------
 // On return (after the caller's next group barrier) sm.list, scratch[kScrNCand|kScrOff|kScrFast] are valid.
-template <int SPS, int FMT, int NT, class GB>
+// UG: loads an edge tile keeps in flight per thread (the latency-path kernel, which runs alone on its SM and has the
+// registers, takes a whole 4096-sample tile in one batch: one PCIe round trip instead of three)
+template <int SPS, int FMT, int NT, class GB, int UG = 6>
 __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const GB gb)
 {
     using G = Geo<SPS, NT>;
@@ -522,14 +524,30 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             }
             gb.sync();
         }
-        for (int k = wid * 32; k < S; k += NT) {
-            const long long i = w0 + k + lane;
-            const float v = (i >= 0 && i < P.win_hi) ? window_x<FMT>(P, i) : 0.0f;
-            bool bit = v >= thr;
-            if (i < 0) bit = P.left_is_start ? (i == -1 && P.prev_bit) : false;
-            sm.mag[k + lane] = v;
-            const unsigned w = __ballot_sync(kFull, bit);
-            if (lane == 0) sm.bits[k >> 5] = w;
+        // loads in batches, issued back to back before the first one is used: on the latency path these are reads of
+        // pinned host memory over PCIe (microseconds each), and a call of GNU Radio size consists of edge tiles only
+        for (int kb = wid * 32; kb < S; kb += NT * UG) {
+            unsigned long long raw[UG];
+            bool have[UG];
+#pragma unroll
+            for (int u = 0; u < UG; u++) {
+                const long long i = w0 + kb + u * NT + lane;
+                raw[u] = 0;
+                have[u] = kb + u * NT < S && i >= 0 && i < P.win_hi && window_raw<FMT>(P, i, raw[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < UG; u++) {
+                const int k = kb + u * NT;
+                if (k < S) {                                     // same for the whole warp
+                    const long long i = w0 + k + lane;
+                    const float v = have[u] ? raw_to_x<FMT>(raw[u]) : 0.0f;
+                    bool bit = v >= thr;
+                    if (i < 0) bit = P.left_is_start ? (i == -1 && P.prev_bit) : false;
+                    sm.mag[k + lane] = v;
+                    const unsigned w = __ballot_sync(kFull, bit);
+                    if (lane == 0) sm.bits[k >> 5] = w;
+                }
+            }
         }
     }
     gb.sync();

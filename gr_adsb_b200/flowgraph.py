@@ -62,5 +62,6 @@ def _pdus_of(msg):
     """A published message is one PDU `(meta, u8[112])` or a batch `(meta{'batch': n, ...}, u8[n,112])`."""
     meta, vec = msg
     if isinstance(meta, dict) and "batch" in meta:
-        return [({"timestamp": meta["timestamp"][i], "snr": meta["snr"][i]}, vec[i]) for i in range(meta["batch"])]
+        bits = np.asarray(vec, dtype=np.uint8).reshape(meta["batch"], 112)
+        return [({"timestamp": meta["timestamp"][i], "snr": meta["snr"][i]}, bits[i]) for i in range(meta["batch"])]
     return [(meta, vec)]

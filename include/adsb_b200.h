@@ -217,6 +217,21 @@ int adsb_shard_write(adsb_ctx *ctx, size_t byte_offset, const void *src, size_t 
 int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold, int phases, int use_graph,
                     void *stream);
 
+/* The latency path.  Calls of GNU Radio size (float32 or complex64 input, at most 64 tiles = 256 Ki items at 2 Msps,
+ * no error correction) do not go through the copy / multi-kernel pipeline: adsb_framer_work, adsb_demod_work and
+ * adsb_burst_work stage the caller's (pageable) buffer through pinned, device-mapped memory, launch ONE kernel that
+ * scans, slices and resolves the call and writes hits and counters back into pinned memory, and spin on its
+ * completion stamp -- same results, same state updates (framer.py:72-182, demod.py:57-136).  adsb_latency_stats:
+ * calls served that way and how many of them had more candidates than the in-kernel resolve holds (finished by the
+ * resolve kernels instead).  adsb_set_latency_path(ctx, 0) forces the throughput pipeline (A/B measurements; the
+ * environment variable ADSB_NO_LATENCY_PATH=1 does the same for every new context). */
+int adsb_latency_stats(const adsb_ctx *ctx, uint64_t *calls, uint64_t *fallbacks);
+int adsb_set_latency_path(adsb_ctx *ctx, int on);
+/* Diagnostics of the latest latency-path call: host3 = seconds spent staging the input, launching, and waiting for the
+ * completion stamp; dev8 = device %globaltimer stamps of the resolving CTA (kernel entry, -, tile detected, sliced,
+ * last-tile ticket, resolved), only filled by builds with -DADSB_SMALL_TIMING=1 (tools/latency_probe.py). */
+int adsb_latency_trace(const adsb_ctx *ctx, uint64_t *dev8, double *host3);
+
 /* Measurement hook for bench.py: when enabled, adsb_burst_work_dev records CUDA events on its launch
  * stream before the scan kernel, after it and after the resolve kernels; adsb_profile_last waits for
  * the last one and returns the two durations in milliseconds. */

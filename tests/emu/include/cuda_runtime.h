@@ -91,6 +91,9 @@ static inline cudaError_t cudaMalloc(void **p, size_t n)
 static inline cudaError_t cudaFree(void *p) { cuda_emu::guarded_free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void *p) { cuda_emu::guarded_free(p); return cudaSuccess; }
+enum { cudaHostAllocMapped = 2, cudaErrorNotReady = 600 };
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
@@ -156,6 +159,7 @@ template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; 
 static inline int atomicCAS(int *p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
 static inline void __threadfence_block() {}
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
 static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline long long atomicMax(long long *p, long long v) { long long o = *p; if (v > o) *p = v; return o; }

@@ -30,6 +30,8 @@ def _defs(*on):
 
 VARIANTS = {
     "default": _defs(),
+    # latency path with %globaltimer stamps per phase (tools/latency_probe.py prints them)
+    "timing": _defs() + ["-DADSB_SMALL_TIMING=1"],
 }
 
 
