@@ -1,9 +1,9 @@
 # Convenience targets; the driver uses __graft_entry__.build() which does the same.
 NVCC ?= nvcc
-NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared
+NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -pthread -shared
 LIB = gr_adsb_b200/csrc/libadsb_b200.so
 SRC = gr_adsb_b200/csrc/adsb_api.cu
-HDR = gr_adsb_b200/csrc/adsb_scan.cuh gr_adsb_b200/csrc/adsb_resolve.cuh gr_adsb_b200/csrc/adsb_device.cuh include/adsb_b200.h
+HDR = gr_adsb_b200/csrc/adsb_scan.cuh gr_adsb_b200/csrc/adsb_resolve.cuh gr_adsb_b200/csrc/adsb_device.cuh gr_adsb_b200/csrc/adsb_small.cuh include/adsb_b200.h
 
 all: $(LIB) oracle/liboracle_adsb.so
 

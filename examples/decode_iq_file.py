@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--max", type=int, default=20, help="messages to print")
     ap.add_argument("--format", default="fc32", choices=["fc32", "sc16", "cu8"], help="sample format of the file")
     ap.add_argument("--synth", type=int, default=0, help="first write a synthetic capture of this many samples")
+    ap.add_argument("--chunk", type=int, default=1 << 26, help="samples per device chunk (three are resident)")
     a = ap.parse_args()
     sps = int(a.fs // 1e6)
     if a.synth:
@@ -40,17 +41,38 @@ def main():
             np.clip(np.round(ri * 128.0 + 127.5), 0, 255).astype(np.uint8).tofile(a.path)
         else:
             d["iq"].tofile(a.path)
-    if a.format == "fc32":
-        iq = np.fromfile(a.path, dtype=np.complex64)
-    else:
-        iq = np.fromfile(a.path, dtype=np.int16 if a.format == "sc16" else np.uint8).reshape(-1, 2)
-    ctx = g.Context(sps, len(iq))
+    # Stream the file through the device: the reads go straight into the context's pinned staging buffer
+    # (adsb_stream_acquire / adsb_stream_commit), chunk k is scanned while chunk k+1 crosses PCIe, and the result is
+    # what ONE framer + demod call over the whole file would give -- for recordings of any size, not just those that fit
+    # in host or device memory.
+    fmt = {"fc32": g.FMT_C64, "sc16": g.FMT_SC16, "cu8": g.FMT_CU8}[a.format]
+    item_bytes = {"fc32": 8, "sc16": 4, "cu8": 2}[a.format]
+    n_items = os.path.getsize(a.path) // item_bytes
+    chunk = max(1 << 14, min(a.chunk, n_items))
+    ctx = g.Context(sps, chunk)
     if a.fec:
         ctx.set_error_correction(g.FEC_CONSERVATIVE)
-    hits = ctx.burst_work(iq, threshold=a.threshold)
-    c = ctx.counters()
-    print("%d samples: %d bursts tagged, %d demodulated, %d pass parity (+%d repaired)" % (
-        len(iq), c["n_hits"], c["n_demod"], c["n_crc_ok"], c["n_fec_fixed"]))
+    ctx.stream_open(fmt, a.threshold, chunk)
+    parts = []
+    with open(a.path, "rb", buffering=0) as f:
+        left = n_items
+        while left:
+            dst = ctx.stream_buffer()                       # free part of the pinned staging buffer
+            want = min(left, len(dst))
+            got = f.readinto(memoryview(dst[:want]).cast("B")) // item_bytes
+            if got == 0:
+                break
+            ctx.stream_commit(got)
+            left -= got
+            parts.append(ctx.stream_pop())
+    ctx.stream_flush()
+    parts.append(ctx.stream_pop())
+    hits = np.concatenate(parts)
+    st = ctx.stream_stats()
+    n_demod = int(((hits["flags"] & g.HIT_DEMOD_VALID) != 0).sum())
+    n_fixed = int(((hits["flags"] & g.HIT_FEC_FIXED) != 0).sum())
+    print("%d samples in %d chunks: %d bursts tagged, %d demodulated, %d pass parity (%d of them repaired)" % (
+        st["items"], st["chunks_done"], len(hits), n_demod, st["crc_ok"], n_fixed))
     ok = hits[(hits["flags"] & g.HIT_CRC_OK) != 0]
     for h, bits in list(zip(ok, g.unpack_bits(ok)))[: a.max]:
         print("  offset %10d  t=%.6f s  snr %5.1f dB  %s%s" % (

@@ -43,7 +43,7 @@ class Counters(C.Structure):
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def build(force=False, verbose=False):
@@ -67,7 +67,9 @@ EXPORTS = ["adsb_strerror", "adsb_abi_version", "adsb_device_count", "adsb_creat
            "adsb_profile_enable", "adsb_profile_last", "adsb_burst_reresolve_dev",
            "adsb_burst_export_carry_dev", "adsb_burst_carry_round_dev", "adsb_set_error_correction",
            "adsb_burst_mag_out", "adsb_shard_alloc", "adsb_shard_attach", "adsb_shard_attach_ptrs", "adsb_shard_detach",
-           "adsb_shard_write", "adsb_shard_step", "adsb_latency_stats", "adsb_set_latency_path", "adsb_latency_trace"]
+           "adsb_shard_write", "adsb_shard_step", "adsb_latency_stats", "adsb_set_latency_path", "adsb_latency_trace", "adsb_stream_open", "adsb_stream_push",
+           "adsb_stream_acquire", "adsb_stream_commit", "adsb_stream_pop", "adsb_stream_flush", "adsb_stream_close",
+           "adsb_stream_stats"]
 
 
 def lib():
@@ -142,6 +144,22 @@ def lib():
     L.adsb_shard_step.argtypes = [vp, i32, sz, f32, i32, i32, vp]
     L.adsb_latency_stats.restype = i32
     L.adsb_latency_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.adsb_stream_open.restype = i32
+    L.adsb_stream_open.argtypes = [vp, i32, f32, sz]
+    L.adsb_stream_push.restype = i32
+    L.adsb_stream_push.argtypes = [vp, vp, sz]
+    L.adsb_stream_acquire.restype = i32
+    L.adsb_stream_acquire.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    L.adsb_stream_commit.restype = i32
+    L.adsb_stream_commit.argtypes = [vp, sz]
+    L.adsb_stream_pop.restype = i32
+    L.adsb_stream_pop.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.adsb_stream_flush.restype = i32
+    L.adsb_stream_flush.argtypes = [vp]
+    L.adsb_stream_close.restype = i32
+    L.adsb_stream_close.argtypes = [vp]
+    L.adsb_stream_stats.restype = i32
+    L.adsb_stream_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     L.adsb_latency_trace.restype = i32
     L.adsb_latency_trace.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.adsb_set_latency_path.restype = i32
@@ -348,6 +366,57 @@ class Context(object):
     def shard_step(self, fmt, shard_items, threshold, phases=SHARD_PH_ALL, use_graph=False, stream=0):
         self._check(lib().adsb_shard_step(self._h, int(fmt), int(shard_items), float(np.float32(threshold)), int(phases),
                                           1 if use_graph else 0, C.c_void_p(stream)))
+
+    # --- streaming session (include/adsb_b200.h: adsb_stream_*) ---------------------------------------------
+    _FMT_DTYPES = {FMT_F32: (np.float32, 1), FMT_C64: (np.complex64, 1), FMT_SC16: (np.int16, 2), FMT_CU8: (np.uint8, 2)}
+
+    def stream_open(self, fmt, threshold, chunk_items):
+        self._check(lib().adsb_stream_open(self._h, int(fmt), float(np.float32(threshold)), int(chunk_items)))
+        self._stream_fmt = int(fmt)
+
+    def stream_push(self, samples):
+        """Append samples (any length): float32 |IQ|^2, complex64, int16[n,2] or uint8[n,2] as the session's format says."""
+        dt, width = self._FMT_DTYPES[self._stream_fmt]
+        a = np.ascontiguousarray(samples, dtype=dt)
+        n = a.size // width
+        self._check(lib().adsb_stream_push(self._h, _ptr(a), n))
+
+    def stream_buffer(self):
+        """The free part of the pinned staging buffer as a NumPy array to fill in place (np.fromfile / readinto);
+        follow with stream_commit(items_written)."""
+        p, cap = C.c_void_p(), C.c_size_t()
+        self._check(lib().adsb_stream_acquire(self._h, C.byref(p), C.byref(cap)))
+        dt, width = self._FMT_DTYPES[self._stream_fmt]
+        n = cap.value * width
+        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=n)
+        return arr.reshape(-1, 2) if width == 2 else arr
+
+    def stream_commit(self, n_items):
+        self._check(lib().adsb_stream_commit(self._h, int(n_items)))
+
+    def stream_pop(self, cap=1 << 16):
+        """Hits completed so far (structured array, possibly empty), in stream order."""
+        out = []
+        while True:
+            hits = np.zeros(cap, HIT_DTYPE)
+            n = C.c_size_t(0)
+            self._check(lib().adsb_stream_pop(self._h, _ptr(hits), cap, C.byref(n)))
+            out.append(hits[:n.value])
+            if n.value < cap:
+                break
+        return np.concatenate(out) if len(out) > 1 else out[0]
+
+    def stream_flush(self):
+        self._check(lib().adsb_stream_flush(self._h))
+
+    def stream_close(self):
+        self._check(lib().adsb_stream_close(self._h))
+
+    def stream_stats(self):
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(lib().adsb_stream_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("items", "chunks_done", "hits", "crc_ok"), (x.value for x in v)))
 
     def latency_stats(self):
         """(calls served by the one-kernel latency path, how many of them fell back to the resolve kernels)"""

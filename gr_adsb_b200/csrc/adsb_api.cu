@@ -7,6 +7,9 @@
 #include <time.h>
 
 #include <new>
+#if !defined(ADSB_HOST_EMU)
+#include <thread>
+#endif
 
 #include "../../include/adsb_b200.h"
 #include "adsb_device.cuh"
@@ -147,6 +150,27 @@ struct adsb_ctx {
         unsigned long long calls, fallbacks;
         double host_t[3];        // seconds: entry -> staged, -> launched, -> stamp seen (latest call)
     } small;
+    // streaming session (adsb_stream_*): one long stream pushed from the host in pieces, whole-stream semantics
+    struct {
+        bool open, flushed;
+        int fmt;
+        float thr;
+        size_t C, isz;               // chunk items, bytes per item
+        void *d_buf[3];              // device chunks k % 3: a chunk's scan reads its left and right neighbour in place
+        size_t d_items[3];
+        void *h_pin[2];              // pinned staging, one chunk each
+        int cur;                     // staging buffer being filled
+        size_t fill;                 // items in it
+        long long submitted;         // chunks handed to the copy engine
+        long long processed;         // chunks scanned + resolved
+        long long collected;         // chunks whose hits are in `out`
+        unsigned long long total_items;
+        long long e_global;          // blanking state after the latest collected chunk (global window index; kCarryNone: none)
+        cudaEvent_t ev_copy[2], ev_h2d[3], ev_scan[3];
+        Rec *out;                    // hits so far
+        size_t out_n, out_cap, out_read;
+        unsigned long long n_cand, n_crc, n_demod;
+    } st;
     Rec *h_tmp;                  // host scratch of the two-block entry points
     size_t h_tmp_cap;
     unsigned char *h_bits;
@@ -725,6 +749,7 @@ void adsb_destroy(adsb_ctx *ctx)
     cudaFree(ctx->d_bits);
     cudaFree(ctx->d_valid);
     cudaFree(ctx->d_mag);
+    adsb_stream_close(ctx);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->small.out) cudaFreeHost(ctx->small.out);
     if (ctx->small.in) cudaFreeHost(ctx->small.in);
@@ -1238,6 +1263,287 @@ int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold,
 #endif
     ctx->shard.steps_plain++;
     return shard_issue(ctx, fmt, shard_items, threshold, phases, s);
+}
+
+
+// ---- streaming session -------------------------------------------------------------------------------------
+namespace {
+
+// pageable -> pinned staging copy: one core moves ~10 GB/s, PCIe takes 50; large pushes are split over a few threads
+void big_memcpy(void *dst, const void *src, size_t bytes)
+{
+#if !defined(ADSB_HOST_EMU)
+    constexpr size_t kPart = 8u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t parts = bytes / kPart;
+    if (parts > 8) parts = 8;
+    if (hw && parts > hw) parts = hw;
+    if (parts >= 2) {
+        std::thread th[8];
+        const size_t per = (bytes / parts + 63) & ~(size_t)63;
+        size_t off = 0;
+        unsigned n = 0;
+        for (; n < parts && off < bytes; n++) {
+            const size_t len = (off + per < bytes && n + 1 < parts) ? per : bytes - off;
+            th[n] = std::thread([=]() { memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
+            off += len;
+        }
+        for (unsigned i = 0; i < n; i++) th[i].join();
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+
+// scan + resolve of chunk k of the stream (k < submitted): its window is [chunk k-1 | chunk k | chunk k+1], read in place
+int stream_process(adsb_ctx *ctx, long long k, bool last, unsigned long long s_tot)
+{
+    auto &S = ctx->st;
+    const long long C = (long long)S.C, h1 = ctx->hist;
+    const bool first = k == 0;
+    const long long n_own = (long long)S.d_items[k % 3];
+    const long long lead = first ? h1 : C;
+    // falls owned: stream index [k*C, min((k+1)*C, s_tot - h1)) -- the last 8*sps-1 items of the stream are look-ahead
+    // only, exactly as in one work() call over the whole stream (framer.py:72-77)
+    long long hi_stream = (k + 1) * C;
+    if (last || (long long)s_tot - h1 < hi_stream) hi_stream = (long long)s_tot - h1;
+    const long long own_lo = first ? 0 : lead;
+    const long long own_hi = lead + (hi_stream - k * C);
+    const long long base = first ? 0 : k * C + h1 - lead;
+    cudaStream_t s = ctx->stream;
+    S.processed = k + 1;
+    if (own_hi <= own_lo) {          // nothing owned (a tail shorter than the look-ahead)
+        ctx->last.pending = false;
+        return ADSB_OK;
+    }
+    const long long n_tiles = tiles_for(ctx, own_hi, lead);
+    if ((size_t)n_tiles > ctx->tile_cap) return fail(ctx, ADSB_E_INVAL, "chunk_items exceeds max_items given to adsb_create");
+    int rc;
+    CK(cudaStreamWaitEvent(s, S.ev_h2d[k % 3], 0));
+    if (!last) CK(cudaStreamWaitEvent(s, S.ev_h2d[(k + 1) % 3], 0));
+    if ((rc = begin_call(ctx, n_tiles, own_hi - lead + 1, s))) return rc;
+    ScanParams P = make_params(ctx, S.d_buf[k % 3], (size_t)n_own, (size_t)lead, (size_t)own_hi, (size_t)own_lo, S.thr, base,
+                               first ? (0.0f >= S.thr) : 0, 1);
+    if (!first) {
+        P.in_left = S.d_buf[(k - 1) % 3];
+        P.left_off = 0;
+    }
+    if (!last) {
+        P.in_right = S.d_buf[(k + 1) % 3];
+        P.n_right = (long long)S.d_items[(k + 1) % 3];
+    }
+    P.win_hi = P.n_loc + P.n_right;
+    CK(launch_scan(ctx, P, S.fmt, 0u, (unsigned)n_tiles, s));
+    const long long eob_in = (S.e_global == kCarryNone) ? -1 - base : S.e_global - base;     // window coordinates of this chunk
+    if ((rc = launch_resolve(ctx, n_tiles, base, eob_in, s))) return rc;
+    CK(cudaEventRecord(S.ev_scan[k % 3], s));
+    ctx->last.pending = true;
+    ctx->last.n_out = own_hi;
+    ctx->last.lead = lead;
+    ctx->last.base = base;
+    ctx->last.eob_in = eob_in;
+    ctx->last.left_is_start = 0;       // a streaming session never touches the framer state of the block entry points
+    ctx->last.stream = s;
+    return ADSB_OK;
+}
+
+// fetch the hits of the chunk processed last into the session's result list
+int stream_collect(adsb_ctx *ctx)
+{
+    auto &S = ctx->st;
+    if (S.collected >= S.processed) return ADSB_OK;
+    S.collected = S.processed;
+    if (!ctx->last.pending) return ADSB_OK;
+    adsb_counters c;
+    size_t n = 0;
+    int rc = adsb_burst_finish(ctx, &c, nullptr, 0, &n);
+    if (rc) return rc;
+    if (S.out_n + n > S.out_cap) {
+        size_t want = S.out_cap ? S.out_cap * 2 : 4096;
+        while (want < S.out_n + n) want *= 2;
+        Rec *p = (Rec *)realloc(S.out, want * sizeof(Rec));
+        if (!p) return fail(ctx, ADSB_E_NOMEM, "realloc(stream hits)");
+        S.out = p;
+        S.out_cap = want;
+    }
+    if (n) {
+        CK(cudaMemcpy(S.out + S.out_n, ctx->d_hits, n * sizeof(Rec), cudaMemcpyDeviceToHost));
+        S.out_n += n;
+    }
+    S.n_cand += c.n_candidates;
+    S.n_crc += c.n_crc_ok + c.n_fec_fixed;
+    S.n_demod += c.n_demod;
+    if (c.last_accept >= 0) S.e_global = ctx->last.base + c.last_accept + 63LL * ctx->sps;
+    ctx->last.pending = false;
+    return ADSB_OK;
+}
+
+// hand the staging buffer being filled (fill items) to the copy engine as the next chunk; scan the chunk before it
+int stream_submit(adsb_ctx *ctx, bool final_chunk)
+{
+    auto &S = ctx->st;
+    const long long j = S.submitted;
+    int rc;
+    // chunk j goes where chunk j-3 was: chunk j-2, whose scan reads that buffer as its left neighbour, must be done
+    if (j >= 3) CK(cudaStreamWaitEvent(ctx->copy_stream, S.ev_scan[(j - 2) % 3], 0));
+    CK(cudaMemcpyAsync(S.d_buf[j % 3], S.h_pin[S.cur], S.fill * S.isz, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(S.ev_copy[S.cur], ctx->copy_stream));
+    CK(cudaEventRecord(S.ev_h2d[j % 3], ctx->copy_stream));
+    S.d_items[j % 3] = S.fill;
+    S.submitted = j + 1;
+    S.cur ^= 1;
+    S.fill = 0;
+    if (j >= 1) {
+        if ((rc = stream_collect(ctx))) return rc;            // chunk j-2 (its header must be read before the next reset)
+        if ((rc = stream_process(ctx, j - 1, false, final_chunk ? S.total_items : ~0ULL >> 1))) return rc;
+    }
+    // the other staging buffer is filled next: its previous copy must have left it
+    CK(cudaEventSynchronize(S.ev_copy[S.cur]));
+    return ADSB_OK;
+}
+
+}  // namespace
+
+int adsb_stream_close(adsb_ctx *ctx)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    auto &S = ctx->st;
+    if (!S.open && !S.out && !S.d_buf[0]) return ADSB_OK;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 3; i++) {
+        cudaFree(S.d_buf[i]);
+        if (S.ev_h2d[i]) cudaEventDestroy(S.ev_h2d[i]);
+        if (S.ev_scan[i]) cudaEventDestroy(S.ev_scan[i]);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (S.h_pin[i]) cudaFreeHost(S.h_pin[i]);
+        if (S.ev_copy[i]) cudaEventDestroy(S.ev_copy[i]);
+    }
+    free(S.out);
+    memset(&S, 0, sizeof(S));
+    ctx->last.pending = false;
+    return ADSB_OK;
+}
+
+int adsb_stream_open(adsb_ctx *ctx, int fmt, float threshold, size_t chunk_items)
+{
+    if (!ctx || fmt < 0 || fmt >= kNumFmt) return ADSB_E_INVAL;
+    if (chunk_items > ctx->max_items) return fail(ctx, ADSB_E_INVAL, "chunk_items exceeds max_items given to adsb_create");
+    if (chunk_items < (size_t)(120 * ctx->sps + 256)) return fail(ctx, ADSB_E_INVAL, "chunk shorter than a burst plus the noise window");
+    ON_DEVICE(ctx);
+    adsb_stream_close(ctx);
+    auto &S = ctx->st;
+    S.fmt = fmt;
+    S.thr = threshold;
+    S.C = chunk_items;
+    S.isz = (fmt == kFmtC64) ? 8 : (fmt == kFmtCU8) ? 2 : 4;
+    S.e_global = kCarryNone;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+        e = cudaMalloc(&S.d_buf[i], S.C * S.isz + 256);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev_scan[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaHostAlloc(&S.h_pin[i], S.C * S.isz, cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev_copy[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        adsb_stream_close(ctx);
+        return fail(ctx, ADSB_E_NOMEM, "stream buffers", e);
+    }
+    S.open = true;
+    return ADSB_OK;
+}
+
+int adsb_stream_acquire(adsb_ctx *ctx, void **host_buf, size_t *cap_items)
+{
+    if (!ctx || !host_buf || !cap_items) return ADSB_E_INVAL;
+    auto &S = ctx->st;
+    if (!S.open || S.flushed) return fail(ctx, ADSB_E_INVAL, "no open stream");
+    *host_buf = static_cast<char *>(S.h_pin[S.cur]) + S.fill * S.isz;
+    *cap_items = S.C - S.fill;
+    return ADSB_OK;
+}
+
+int adsb_stream_commit(adsb_ctx *ctx, size_t n_items)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    auto &S = ctx->st;
+    if (!S.open || S.flushed) return fail(ctx, ADSB_E_INVAL, "no open stream");
+    if (n_items > S.C - S.fill) return fail(ctx, ADSB_E_INVAL, "adsb_stream_commit: more than adsb_stream_acquire offered");
+    ON_DEVICE(ctx);
+    S.fill += n_items;
+    S.total_items += n_items;
+    if (S.fill == S.C) return stream_submit(ctx, false);
+    return ADSB_OK;
+}
+
+int adsb_stream_push(adsb_ctx *ctx, const void *samples, size_t n_items)
+{
+    if (!ctx || (!samples && n_items)) return ADSB_E_INVAL;
+    auto &S = ctx->st;
+    if (!S.open || S.flushed) return fail(ctx, ADSB_E_INVAL, "no open stream");
+    const char *src = static_cast<const char *>(samples);
+    while (n_items) {
+        void *dst;
+        size_t cap;
+        int rc = adsb_stream_acquire(ctx, &dst, &cap);
+        if (rc) return rc;
+        const size_t n = n_items < cap ? n_items : cap;
+        big_memcpy(dst, src, n * S.isz);
+        if ((rc = adsb_stream_commit(ctx, n))) return rc;
+        src += n * S.isz;
+        n_items -= n;
+    }
+    return ADSB_OK;
+}
+
+int adsb_stream_flush(adsb_ctx *ctx)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    auto &S = ctx->st;
+    if (!S.open) return fail(ctx, ADSB_E_INVAL, "no open stream");
+    if (S.flushed) return ADSB_OK;
+    ON_DEVICE(ctx);
+    int rc;
+    if (S.fill > 0) {
+        if ((rc = stream_submit(ctx, true))) return rc;       // also scans the chunk before it, with the true stream end
+    }
+    S.flushed = true;
+    if (S.submitted == 0) return ADSB_OK;
+    if ((rc = stream_collect(ctx))) return rc;
+    if (S.processed < S.submitted) {
+        if ((rc = stream_process(ctx, S.submitted - 1, true, S.total_items))) return rc;
+        if ((rc = stream_collect(ctx))) return rc;
+    }
+    return ADSB_OK;
+}
+
+int adsb_stream_pop(adsb_ctx *ctx, adsb_hit *hits, size_t cap, size_t *n_hits)
+{
+    if (!ctx || !n_hits || (!hits && cap)) return ADSB_E_INVAL;
+    auto &S = ctx->st;
+    if (!S.open) return fail(ctx, ADSB_E_INVAL, "no open stream");
+    size_t n = S.out_n - S.out_read;
+    if (n > cap) n = cap;
+    if (n) memcpy(hits, S.out + S.out_read, n * sizeof(Rec));
+    S.out_read += n;
+    *n_hits = n;
+    return ADSB_OK;
+}
+
+int adsb_stream_stats(const adsb_ctx *ctx, uint64_t *items, uint64_t *chunks_done, uint64_t *hits, uint64_t *crc_ok)
+{
+    if (!ctx) return ADSB_E_INVAL;
+    const auto &S = ctx->st;
+    if (items) *items = S.total_items;
+    if (chunks_done) *chunks_done = (uint64_t)S.collected;
+    if (hits) *hits = S.out_n;
+    if (crc_ok) *crc_ok = S.n_crc;
+    return ADSB_OK;
 }
 
 int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits)

@@ -217,6 +217,34 @@ int adsb_shard_write(adsb_ctx *ctx, size_t byte_offset, const void *src, size_t 
 int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold, int phases, int use_graph,
                     void *stream);
 
+/* ---- Streaming session: one long recording / SDR stream pushed from the host in pieces ---------------------------------
+ * (the ingest side of examples/adsb_rx.py:113-126,180.)  Result = ONE framer.work() + demod.work() call over
+ * the whole stream (framer.py:72-182, demod.py:57-136), whatever the sizes of the pushes, for streams far larger than
+ * device memory.  The context keeps two pinned staging buffers and three device buffers of `chunk_items`: while chunk
+ * k+1 travels over PCIe, chunk k is scanned with its neighbours k-1 and k+1 read in place (noise window and pulse-run
+ * look-back to the left, preamble + 112 bits to the right -- no overlap is copied twice) and the blanking state
+ * (framer.py:121-123,165) is handed from chunk to chunk.  Sample formats as adsb_burst_work (int16 / uint8 IQ are
+ * widened on the device: half / a quarter of the PCIe bytes).
+ *   adsb_stream_open     start a session (ends any previous one); chunk_items <= max_items of adsb_create
+ *   adsb_stream_push     append n_items samples from any host memory (copied into the pinned staging buffer)
+ *   adsb_stream_acquire  ... or get the free part of the staging buffer to fill in place (fread, SDR driver), then
+ *   adsb_stream_commit   say how many items were written; a full buffer is sent off, the call returns when the other
+ *                        staging buffer is free again
+ *   adsb_stream_pop      hits completed so far, in stream order (idx = stream index + 8*sps-1, as adsb_burst_work with
+ *                        lead = 8*sps-1); never blocks
+ *   adsb_stream_flush    end of stream: scan what is buffered with the tail semantics of the single call (the last
+ *                        8*sps-1 items are look-ahead only; bursts that do not end inside the stream are not demodulated)
+ *   adsb_stream_close    free the session's buffers (adsb_destroy does it too)
+ * The session uses the context's device buffers: do not interleave other entry points of the same context. */
+int adsb_stream_open(adsb_ctx *ctx, int fmt, float threshold, size_t chunk_items);
+int adsb_stream_push(adsb_ctx *ctx, const void *samples, size_t n_items);
+int adsb_stream_acquire(adsb_ctx *ctx, void **host_buf, size_t *cap_items);
+int adsb_stream_commit(adsb_ctx *ctx, size_t n_items);
+int adsb_stream_pop(adsb_ctx *ctx, adsb_hit *hits, size_t cap, size_t *n_hits);
+int adsb_stream_flush(adsb_ctx *ctx);
+int adsb_stream_close(adsb_ctx *ctx);
+int adsb_stream_stats(const adsb_ctx *ctx, uint64_t *items, uint64_t *chunks_done, uint64_t *hits, uint64_t *crc_ok);
+
 /* The latency path.  Calls of GNU Radio size (float32 or complex64 input, at most 64 tiles = 256 Ki items at 2 Msps,
  * no error correction) do not go through the copy / multi-kernel pipeline: adsb_framer_work, adsb_demod_work and
  * adsb_burst_work stage the caller's (pageable) buffer through pinned, device-mapped memory, launch ONE kernel that
