@@ -79,10 +79,12 @@ def lib():
     if "ADSB_B200_LIB" not in os.environ:
         try:
             build()           # no-op when the in-tree library is newer than its sources
-        except Exception as e:
+        except FileNotFoundError as e:
+            # no nvcc on this machine (a GPU box that received the prebuilt library with the snapshot): use what is there
             if not os.path.isfile(LIB_PATH):
-                raise RuntimeError("%s is not built and nvcc failed (%s): run "
-                                   "`python -c 'import __graft_entry__ as g; g.build()'`" % (LIB_PATH, e))
+                raise RuntimeError("%s is not built and there is no nvcc here (%s): run "
+                                   "`python -c 'import __graft_entry__ as g; g.build()'` where the CUDA toolkit is" % (LIB_PATH, e))
+        # a compile error (CalledProcessError) propagates: running on a stale library after an edit would test old kernels
     if not os.path.isfile(LIB_PATH):
         raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
     L = C.CDLL(LIB_PATH)

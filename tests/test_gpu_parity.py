@@ -171,7 +171,7 @@ def test_device_resident_entry_point():
 def test_full_size_properties():
     """BASELINE config-2 shape at 2^26 samples, generated in HBM: every injected burst that is clear of
     its neighbours must come back with exactly its bits and a passing CRC; hits are ordered and obey
-    the 63-symbol blanking; all of it twice (determinism)."""
+    the 63-symbol blanking; all of it twice (determinism); and the ~100 000 hits equal the C oracle's exactly."""
     torch = pytest.importorskip("torch")
     n, sps, thr = 1 << (21 if devmem.EMU else 26), 2, 0.01      # the emulation runs ~0.4 Msamples/s
     nb = int(n * 5e-3)
@@ -203,6 +203,19 @@ def test_full_size_properties():
     ok = (hits["flags"][pos[found]] & g.HIT_CRC_OK) != 0
     assert np.array_equal(ok, same | ok) and ok.sum() >= same.sum()
     assert cnt["n_crc_ok"] >= int(same.sum())
+    # and exact equality with the oracle at this size: every tag offset, SNR, PDU and parity verdict of the whole buffer
+    x = co.mag2(iq.cpu().numpy().view(np.complex64).reshape(-1))
+    ref = co.run_stream(x, sps * 1e6, thr, None)
+    H1 = 8 * sps - 1
+    assert np.array_equal(hits["idx"] - H1, ref["tag_off"])
+    a, b = hits["snr"], ref["tag_snr"]
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b))
+    assert np.all(np.abs(a[fin] - b[fin]) <= 1e-4)          # BASELINE.json north_star: SNR within 1e-4 dB
+    valid = (hits["flags"] & g.HIT_DEMOD_VALID) != 0
+    assert np.array_equal(hits["idx"][valid] - H1, ref["pdu_off"])
+    assert np.array_equal(g.unpack_bits(hits[valid]), ref["pdu_bits"])
+    assert cnt["n_crc_ok"] == co.crc_pass_count(ref["pdu_bits"]) and cnt["n_demod"] == len(ref["pdu_off"])
     ctx.close()
 
 
