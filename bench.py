@@ -330,6 +330,11 @@ class PeerStepper(object):
     def step(self, stream, items=None, graph=True):
         self.ctx.shard_step(self.fmt, items or self.L, THRESHOLD, use_graph=graph, stream=stream)
 
+    def check(self, stream, items=None):
+        """The outcome of the latest exchange (a step's own check rides on the next step: ADSB_SHARD_PH_ALL)."""
+        if self.world > 1:
+            self.ctx.shard_step(self.fmt, items or self.L, THRESHOLD, phases=self.g.SHARD_PH_CHECK, stream=stream)
+
     def extra_round(self, stream, items=None):
         g = self.g
         self.ctx.shard_step(self.fmt, items or self.L, THRESHOLD, phases=g.SHARD_PH_EXPORT | g.SHARD_PH_PLAN | g.SHARD_PH_CHECK,
@@ -582,6 +587,7 @@ def main():
     if not args.no_verify and stepper.name == "peer":
         Lv = min(L, 1 << 24)
         stepper.step(sptr, items=Lv, graph=False)
+        stepper.check(sptr, items=Lv)
         for extra in range(world + 1):
             torch.cuda.synchronize()
             c, h = ctx.burst_finish(cap=Lv // (63 * SPS) + 8)
@@ -650,6 +656,8 @@ def main():
     for _ in range(args.steps):
         stepper.step(sptr)
     ev1.record(stream)
+    if stepper.name == "peer":
+        stepper.check(sptr)          # the last step's carry check (every other step's rode on its successor)
     sync_all()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)

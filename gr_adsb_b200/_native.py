@@ -25,7 +25,7 @@ FMT_F32, FMT_C64, FMT_SC16, FMT_CU8 = 0, 1, 2, 3
 CARRY_USED_ON_DEVICE = -(1 << 63)
 E_PEER = -8
 SHARD_CTRL_BYTES, IPC_HANDLE_BYTES = 8192, 64
-SHARD_PH_SIGNAL, SHARD_PH_SCAN, SHARD_PH_EXPORT, SHARD_PH_PLAN, SHARD_PH_CHECK, SHARD_PH_ALL = 1, 2, 4, 8, 16, 31
+SHARD_PH_SIGNAL, SHARD_PH_SCAN, SHARD_PH_EXPORT, SHARD_PH_PLAN, SHARD_PH_CHECK, SHARD_PH_ALL = 1, 2, 4, 8, 16, 15
 
 HIT_DTYPE = np.dtype([("idx", "<i8"), ("snr", "<f4"), ("flags", "<u4"), ("bits", "u1", (16,))], align=True)
 assert HIT_DTYPE.itemsize == 32

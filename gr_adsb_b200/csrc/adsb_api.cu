@@ -111,6 +111,7 @@ struct adsb_ctx {
     size_t staged_n;
     bool small_configured[2];    // latency-path kernel attributes set (float32 / complex64 input)
     int small_fmt;
+    int early_tile;              // ADSB_EARLY_TILE=0 in the environment: the final tile is scanned last, not second (A/B)
     int no_small;                // ADSB_NO_LATENCY_PATH=1 in the environment: always take the throughput pipeline (A/B, debugging)
     bool scan_configured[kNumFmt];  // per sample format: shared-memory attributes of the scan kernel set on this device
     // multi-GPU peer mode (adsb_shard_*): symmetric allocation [ShardCtrl | samples] of every rank, mapped here
@@ -321,6 +322,8 @@ cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned til
     ScanParams P = P0;
     P.tile_first = tile_first;
     P.n_tiles_launch = n_blocks;
+    // a launch that ends with the stream's final tile starts that tile early (see ScanParams::early_tile)
+    P.early_tile = (c->early_tile && n_blocks >= 8 && (long long)tile_first + n_blocks == P.n_tiles_total) ? tile_first + n_blocks - 1 : 0u;
     bool *configured = &c->scan_configured[fmt];
     return launch_scan_s<kThreads>(c->sps, P, fmt, n_blocks, s, configured);
 }
@@ -392,7 +395,7 @@ ScanParams make_params(const adsb_ctx *c, const void *d_in, size_t n_in, size_t 
 }
 
 int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long eob_in, cudaStream_t s, bool rerun = false,
-                   bool dev_carry = false)
+                   bool dev_carry = false, bool reset_done = false)
 {
     ResolveParams R;
     memset(&R, 0, sizeof(R));
@@ -415,10 +418,11 @@ int launch_resolve(adsb_ctx *ctx, long long n_tiles, long long base, long long e
     const unsigned cap_blocks = (unsigned)ctx->num_sms * 4u;
     const unsigned gblocks = (unsigned)(gchunks < cap_blocks ? gchunks : cap_blocks);
     const unsigned cblocks = cap_blocks;
-    if (rerun)
-        ADSB_LAUNCH(reset_resolve_kernel, 1, 1, 0, s, ctx->d_hdr, R.dev_carry);
-    else
+    if (rerun) {
+        if (!reset_done) ADSB_LAUNCH(reset_resolve_kernel, 1, 1, 0, s, ctx->d_hdr, R.dev_carry);
+    } else {
         ADSB_LAUNCH(gather_kernel, gblocks, kThreads, 0, s, R);
+    }
     ADSB_LAUNCH(chain_kernel, cap_blocks, kThreads, 0, s, R);
     ADSB_LAUNCH(compact_kernel, cblocks, kThreads, 0, s, R);
     if (ctx->fec_mode == ADSB_FEC_CONSERVATIVE) {
@@ -804,6 +808,8 @@ int adsb_create(adsb_ctx **out, int device, int sps, size_t max_items)
     {
         const char *e = getenv("ADSB_NO_LATENCY_PATH");
         ctx->no_small = (e && e[0] == '1') ? 1 : 0;
+        e = getenv("ADSB_EARLY_TILE");
+        ctx->early_tile = (e && e[0] == '0') ? 0 : 1;
     }
 
     auto die = [&](int code, const char *what, cudaError_t e) {
@@ -1200,18 +1206,20 @@ int shard_issue(adsb_ctx *ctx, int fmt, size_t items, float threshold, int phase
         const long long blank = 63LL * ctx->sps;
         if ((ph_exp || ph_plan || ph_check) && !ctx->last.pending)
             return fail(ctx, ADSB_E_INVAL, "adsb_shard_step: carry phase without a scan phase");
-        // round 0: export the latest resolve's summary to every rank / wait for everyone's and plan
+        // round 0: (look at the outcome of the previous exchange,) export the latest resolve's summary to every rank /
+        // wait for everyone's and plan
         if (ph_exp || ph_plan)
             ADSB_LAUNCH(shard_carry_kernel, 1, kMaxWorld, 0, s, ctx->d_hdr, own, pc, world, rank, base, blank, 0, ph_exp ? 1 : 0,
-                        ph_plan ? 1 : 0);
+                        ph_plan ? 1 : 0, ph_exp ? 1 : 0);
         if (ph_plan) {
             if ((rc = zero_cand_totals(ctx, ctx->last.n_out - ctx->last.lead + 1, s))) return rc;
-            if ((rc = launch_resolve(ctx, n_tiles, base, 0, s, true, true))) return rc;    // no-ops unless carry_need
+            if ((rc = launch_resolve(ctx, n_tiles, base, 0, s, true, true, /*reset_done=*/true))) return rc;   // no-ops unless carry_need
         }
-        // round 1: the same exchange after the fix-ups, only to check that nothing is left to fix
+        // round 1: the same exchange after the fix-ups, only to check that nothing is left to fix; the check itself waits
+        // for the next exchange (or an explicit CHECK phase) so that it costs the step no second rendezvous
         if (ph_plan || ph_check)
             ADSB_LAUNCH(shard_carry_kernel, 1, kMaxWorld, 0, s, ctx->d_hdr, own, pc, world, rank, base, blank, 1, ph_plan ? 1 : 0,
-                        ph_check ? 1 : 0);
+                        ph_check ? 1 : 0, 0);
         CK(cudaGetLastError());
     }
     return ADSB_OK;
@@ -1221,7 +1229,7 @@ int shard_issue(adsb_ctx *ctx, int fmt, size_t items, float threshold, int phase
 
 int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold, int phases, int use_graph, void *stream)
 {
-    if (!ctx || fmt < 0 || fmt >= kNumFmt || shard_items == 0 || !(phases & ADSB_SHARD_PH_ALL)) return ADSB_E_INVAL;
+    if (!ctx || fmt < 0 || fmt >= kNumFmt || shard_items == 0 || !(phases & (ADSB_SHARD_PH_ALL | ADSB_SHARD_PH_CHECK))) return ADSB_E_INVAL;
     if (!ctx->shard.world) return fail(ctx, ADSB_E_INVAL, "adsb_shard_step: attach first");
     if (shard_items > ctx->max_items) return fail(ctx, ADSB_E_INVAL, "shard_items exceeds max_items given to adsb_create");
     if (shard_items < (size_t)(120 * ctx->sps + 256)) return fail(ctx, ADSB_E_INVAL, "shard shorter than a burst plus the noise window");

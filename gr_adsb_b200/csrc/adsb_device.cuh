@@ -92,6 +92,10 @@ struct ScanParams {
     unsigned tile_first;   // first tile of this launch (blockIdx.x is added)
     unsigned n_tiles_launch;  // tiles covered by this launch
     unsigned prefetch_tiles;  // L2 prefetch distance in tiles (0 = off)
+    unsigned early_tile;      // this tile is scanned by the launch's second CTA instead of its last (0 = off): the stream's
+                              // final tile takes the slow edge path (and, in multi-GPU peer mode, reads a neighbour's memory
+                              // over NVLink) -- started first, its latency hides behind the interior tiles instead of
+                              // forming the kernel's tail
     unsigned fast_lo;      // tiles [fast_lo, fast_lo + fast_span] lie fully inside the array and the owned range
     unsigned fast_span;    // (0xffffffff when there is none)
     int do_demod;

@@ -273,7 +273,8 @@ struct ShardCtrl {
     unsigned long long ready[2];      // step counter of the left [0] / right [1] neighbour, written by that neighbour
     unsigned long long step;          // this rank's step counter
     unsigned long long xchg;          // this rank's carry-exchange counter (one per round-0 export; stamps the slots)
-    unsigned long long pad[4];
+    unsigned long long checked;       // the latest exchange whose outcome (round 1) this rank has evaluated
+    unsigned long long pad[3];
     long long slot[2][kMaxWorld][4];  // [round][rank] = first candidate, last hit, incoming state assumed, step stamp
 };
 static_assert(sizeof(ShardCtrl) <= 8192, "control block must fit ADSB_SHARD_CTRL_BYTES");
@@ -309,46 +310,13 @@ __global__ void shard_sync_kernel(ShardCtrl *own, ShardCtrl *left, ShardCtrl *ri
 // plan: wait until all `world` slots of the own block carry this step's stamp, then evaluate the same plan as
 // gr_adsb_b200/sharding.py:carry_plan.  round 0 arms the conditional re-resolve (chain + compact) that follows on the
 // stream; round 1 only checks that nothing is left to fix (Header.carry_unstable otherwise).
-__global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, ShardCtrl *own, const PeerCtrls peers, int world,
-                                                                 int rank, long long base, long long blank, int round,
-                                                                 int do_export, int do_plan)
+__device__ __forceinline__ bool carry_plan_any(const ShardCtrl *own, int round, int world, int rank, long long blank,
+                                               long long &my_e, int &my_need)
 {
-    const int t = threadIdx.x;
-    // every rank runs the same sequence of exchanges, so the counters agree without being communicated
-    __shared__ unsigned long long s_k;
-    if (t == 0) {
-        unsigned long long x = own->xchg;
-        if (do_export && round == 0) own->xchg = ++x;
-        s_k = x;
-    }
-    __syncthreads();
-    const unsigned long long k = s_k;
-    if (do_export && t < world) {
-        long long *dst = peers.p[t]->slot[round][rank];
-        volatile long long *vd = dst;
-        vd[0] = h->first_cand >= 0 ? base + h->first_cand : kCarryNone;
-        vd[1] = h->last_accept >= 0 ? base + h->last_accept : kCarryNone;
-        vd[2] = h->carry_used;
-        fence_system();
-        vd[3] = (long long)k;
-    }
-    if (!do_plan) return;
-    __shared__ int s_bad;
-    if (t == 0) s_bad = 0;
-    __syncthreads();
-    if (t < world) {
-        if (!wait_ge(reinterpret_cast<const unsigned long long *>(&own->slot[round][t][3]), k)) s_bad = 1;
-        fence_system();
-    }
-    __syncthreads();
-    if (t != 0) return;
-    if (s_bad) {
-        atomicOr(&h->flags, kFlagPeerTimeout);
-        h->carry_need = 0;
-        return;
-    }
-    long long e = kCarryNone, my_e = kCarryNone;
-    int my_need = 0, any = 0;
+    long long e = kCarryNone;
+    int any = 0;
+    my_e = kCarryNone;
+    my_need = 0;
     for (int r = 0; r < world; r++) {
         const volatile long long *sl = own->slot[round][r];
         const long long first = sl[0], last = sl[1], used = sl[2];
@@ -362,13 +330,101 @@ __global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, Shard
         any |= need;
         if (last != kCarryNone) e = last + blank;
     }
+    return any != 0;
+}
+
+// round 0: do_export publishes this rank's summary, do_plan waits for everybody's and arms the conditional re-resolve.
+// round 1: do_export re-publishes after the fix-ups; the CHECK that nothing is left to fix (Header.carry_unstable
+// otherwise) does not sit on the step's critical path: it is made at the start of the NEXT exchange (do_prev_check, before
+// this rank publishes again -- nobody can overwrite a round-1 slot before every rank has published the next round 0), or
+// by an explicit round-1 do_plan call (the end of a run, tests).
+// wait for every rank's round-1 slot of exchange x and count the exchange as unstable if some rank still needs a fix-up
+__device__ __forceinline__ void carry_check(Header *h, ShardCtrl *own, int world, int rank, long long blank,
+                                            unsigned long long x, int *s_bad)
+{
+    const int t = threadIdx.x;
+    if (t == 0) *s_bad = 0;
+    __syncthreads();
+    if (t < world && !wait_ge(reinterpret_cast<const unsigned long long *>(&own->slot[1][t][3]), x)) *s_bad = 1;
+    fence_system();
+    __syncthreads();
+    if (t == 0) {
+        if (*s_bad) {
+            atomicOr(&h->flags, kFlagPeerTimeout);
+        } else {
+            long long e_;
+            int n_;
+            if (carry_plan_any(own, 1, world, rank, blank, e_, n_)) h->carry_unstable += 1;
+        }
+        own->checked = x;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, ShardCtrl *own, const PeerCtrls peers, int world,
+                                                                 int rank, long long base, long long blank, int round,
+                                                                 int do_export, int do_plan, int do_prev_check)
+{
+    const int t = threadIdx.x;
+    __shared__ unsigned long long s_k, s_chk;
+    __shared__ int s_bad;
+    if (t == 0) {
+        s_k = own->xchg;
+        s_chk = own->checked;
+    }
+    __syncthreads();
+    // (A) the outcome of the previous exchange, looked at before this rank publishes again
+    if (do_prev_check && round == 0 && s_k > s_chk) carry_check(h, own, world, rank, blank, s_k, &s_bad);
+    // (B) publish; every rank runs the same sequence of exchanges, so the counters agree without being communicated
+    if (t == 0) {
+        unsigned long long x = own->xchg;
+        if (do_export && round == 0) own->xchg = ++x;
+        s_k = x;
+        s_chk = own->checked;
+        s_bad = 0;
+    }
+    __syncthreads();
+    const unsigned long long k = s_k;
+    if (do_export && t < world) {
+        long long *dst = peers.p[t]->slot[round][rank];
+        volatile long long *vd = dst;
+        vd[0] = h->first_cand >= 0 ? base + h->first_cand : kCarryNone;
+        vd[1] = h->last_accept >= 0 ? base + h->last_accept : kCarryNone;
+        vd[2] = h->carry_used;
+        fence_system();
+        vd[3] = (long long)k;
+    }
+    if (!do_plan) return;
     if (round == 1) {
-        if (any) h->carry_unstable += 1;
+        // (C1) explicit check of this exchange (end of a run, tests)
+        if (k > s_chk) carry_check(h, own, world, rank, blank, k, &s_bad);
+        if (t == 0) h->carry_need = 0;
+        return;
+    }
+    // (C0) wait for everybody's round-0 summary and plan this rank's fix-up
+    if (t < world) {
+        if (!wait_ge(reinterpret_cast<const unsigned long long *>(&own->slot[0][t][3]), k)) s_bad = 1;
+        fence_system();
+    }
+    __syncthreads();
+    if (t != 0) return;
+    if (s_bad) {
+        atomicOr(&h->flags, kFlagPeerTimeout);
         h->carry_need = 0;
-    } else {
-        h->carry_need = my_need;
-        h->carry_ein = my_e;
-        h->carry_used = my_e;       // where no re-run is needed the result is the same under either value
+        return;
+    }
+    long long my_e;
+    int my_need;
+    carry_plan_any(own, 0, world, rank, blank, my_e, my_need);
+    h->carry_need = my_need;
+    h->carry_ein = my_e;
+    h->carry_used = my_e;       // where no re-run is needed the result is the same under either value
+    if (my_need) {              // what reset_resolve_kernel does, for the conditional chain + compact that follow
+        h->n_hits = 0;
+        h->n_demod = 0;
+        h->n_crc = 0;
+        h->last_accept = -1;
+        h->n_fec = 0;
     }
 }
 

@@ -964,7 +964,11 @@ scan_slice_kernel(const ScanParams P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
     const TileSmem sm = carve(smem_raw, Geo<SPS, NT>::T, SPS ? Geo<SPS, NT>::RH : P.rh);
-    const long long tile = (long long)P.tile_first + blockIdx.x;
+    long long tile = (long long)P.tile_first + blockIdx.x;
+    if (P.early_tile) {                 // CTA 1 <-> the CTA of the final tile
+        if (blockIdx.x == 1) tile = P.early_tile;
+        else if (tile == (long long)P.early_tile) tile = (long long)P.tile_first + 1;
+    }
     const CtaBar gb;
     scan_tile<SPS, FMT, NT>(P, sm, tile, gb);
     gb.sync();

@@ -191,7 +191,7 @@ int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int wor
  *   adsb_shard_step         one step over this rank's `shard_items` samples of format `fmt` (ADSB_FMT_*), asynchronous
  *                           on `stream`; every rank calls it with the same arguments.  phases = ADSB_SHARD_PH_ALL runs
  *                           the whole step; the individual bits exist so that a single process driving several ranks
- *                           (tests) can interleave them, and EXPORT|PLAN|CHECK repeats the carry exchange when
+ *                           (tests) can interleave them, and EXPORT|PLAN (then CHECK) repeats the carry exchange when
  *                           adsb_counters.carry_unstable reports that one round was not enough (cascade through
  *                           several shards).  use_graph != 0 replays the step as a captured CUDA graph.
  *   results                 adsb_burst_finish (counters, hits with global window indices); the carried framer state of
@@ -206,7 +206,9 @@ int adsb_burst_carry_round_dev(adsb_ctx *ctx, const int64_t *d_gathered, int wor
 #define ADSB_SHARD_PH_EXPORT 4   /* publish (first candidate, last hit, state assumed) to every rank                 */
 #define ADSB_SHARD_PH_PLAN   8   /* wait for every rank's, re-resolve if the true incoming state demands, re-publish */
 #define ADSB_SHARD_PH_CHECK  16  /* wait for every rank's, count the step as unstable if a fix-up is still needed     */
-#define ADSB_SHARD_PH_ALL    31
+#define ADSB_SHARD_PH_ALL    15  /* one step.  The CHECK of a step is made by the next step's EXPORT (it then costs no second
+                                    rendezvous), so adsb_counters.carry_unstable lags one step: after the last step of a run
+                                    issue ADSB_SHARD_PH_CHECK once before reading it. */
 int adsb_shard_alloc(adsb_ctx *ctx, size_t sample_bytes, void **d_samples, void *ipc_handle);
 int adsb_shard_attach(adsb_ctx *ctx, int rank, int world, const void *ipc_handles);
 int adsb_shard_attach_ptrs(adsb_ctx *ctx, int rank, int world, void *const *peer_bases);
