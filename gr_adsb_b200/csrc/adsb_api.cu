@@ -323,7 +323,7 @@ cudaError_t launch_scan(adsb_ctx *c, const ScanParams &P0, int fmt, unsigned til
     P.tile_first = tile_first;
     P.n_tiles_launch = n_blocks;
     // a launch that ends with the stream's final tile starts that tile early (see ScanParams::early_tile)
-    P.early_tile = (c->early_tile && n_blocks >= 8 && (long long)tile_first + n_blocks == P.n_tiles_total) ? tile_first + n_blocks - 1 : 0u;
+    P.early_tile = (c->early_tile && n_blocks >= 8 && (long long)tile_first + n_blocks == P.n_tiles_total) ? n_blocks - 1 : 0u;
     bool *configured = &c->scan_configured[fmt];
     return launch_scan_s<kThreads>(c->sps, P, fmt, n_blocks, s, configured);
 }

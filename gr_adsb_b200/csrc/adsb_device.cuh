@@ -92,7 +92,7 @@ struct ScanParams {
     unsigned tile_first;   // first tile of this launch (blockIdx.x is added)
     unsigned n_tiles_launch;  // tiles covered by this launch
     unsigned prefetch_tiles;  // L2 prefetch distance in tiles (0 = off)
-    unsigned early_tile;      // this tile is scanned by the launch's second CTA instead of its last (0 = off): the stream's
+    unsigned early_tile;      // the launch's CTA with this index swaps tiles with CTA 1 (0 = off): the stream's
                               // final tile takes the slow edge path (and, in multi-GPU peer mode, reads a neighbour's memory
                               // over NVLink) -- started first, its latency hides behind the interior tiles instead of
                               // forming the kernel's tail

@@ -964,11 +964,12 @@ scan_slice_kernel(const ScanParams P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
     const TileSmem sm = carve(smem_raw, Geo<SPS, NT>::T, SPS ? Geo<SPS, NT>::RH : P.rh);
-    long long tile = (long long)P.tile_first + blockIdx.x;
-    if (P.early_tile) {                 // CTA 1 <-> the CTA of the final tile
-        if (blockIdx.x == 1) tile = P.early_tile;
-        else if (tile == (long long)P.early_tile) tile = (long long)P.tile_first + 1;
-    }
+    // CTA 1 <-> the CTA of the launch's final tile (ScanParams::early_tile); all in 32-bit uniform arithmetic
+    unsigned bx = blockIdx.x;
+    const unsigned eb = P.early_tile;
+    const unsigned sw = (bx == 1u) ? eb : ((bx == eb) ? 1u : bx);
+    bx = eb ? sw : bx;
+    const long long tile = (long long)(P.tile_first + bx);
     const CtaBar gb;
     scan_tile<SPS, FMT, NT>(P, sm, tile, gb);
     gb.sync();
