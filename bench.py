@@ -320,7 +320,7 @@ class PeerStepper(object):
         self.ptr = sharding.peer_attach(self.ctx, dist, rank, world, L * FMT_BYTES[fmt])
         self.transport = ("edge tiles read the neighbours' shards in place over NVLink (CUDA IPC), blanking carry in "
                           "peer-written slots, one CUDA graph per step; no NCCL call in the step")
-        self.launches_per_step = 5 if world == 1 else 11
+        self.launches_per_step = 5 if world == 1 else 10     # init, scan, gather, chain, compact (+ signal, carry x2, chain, compact)
 
     def load(self, tensor):
         import torch
