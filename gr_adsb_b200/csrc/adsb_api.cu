@@ -11,6 +11,10 @@
 #include <thread>
 #endif
 
+#if !defined(ADSB_HOST_EMU)
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+#endif
+
 #include "../../include/adsb_b200.h"
 #include "adsb_device.cuh"
 #include "adsb_resolve.cuh"
@@ -207,6 +211,17 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// one NVTX range per entry point (nsys / ncu --nvtx timelines show the C-ABI calls the blocks make)
+struct NvtxRange {
+#if !defined(ADSB_HOST_EMU)
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char *) {}
+#endif
+};
+#define ADSB_RANGE(name) NvtxRange nvtx_range_(name)
 
 #define ON_DEVICE(ctx)                                                               \
     DeviceGuard guard_((ctx)->device);                                               \
@@ -961,6 +976,7 @@ int adsb_burst_work_dev(adsb_ctx *ctx, const void *d_in, int is_c64, size_t n_in
                         size_t halo_left, float threshold, int64_t base, int64_t eob_in, void *stream,
                         const adsb_hit **d_hits)
 {
+    ADSB_RANGE("adsb_burst_work_dev");
     if (!ctx || !d_in || is_c64 < 0 || is_c64 >= kNumFmt) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, halo_left, true);
     if (rc) return rc;
@@ -1229,6 +1245,7 @@ int shard_issue(adsb_ctx *ctx, int fmt, size_t items, float threshold, int phase
 
 int adsb_shard_step(adsb_ctx *ctx, int fmt, size_t shard_items, float threshold, int phases, int use_graph, void *stream)
 {
+    ADSB_RANGE("adsb_shard_step");
     if (!ctx || fmt < 0 || fmt >= kNumFmt || shard_items == 0 || !(phases & (ADSB_SHARD_PH_ALL | ADSB_SHARD_PH_CHECK))) return ADSB_E_INVAL;
     if (!ctx->shard.world) return fail(ctx, ADSB_E_INVAL, "adsb_shard_step: attach first");
     if (shard_items > ctx->max_items) return fail(ctx, ADSB_E_INVAL, "shard_items exceeds max_items given to adsb_create");
@@ -1478,6 +1495,7 @@ int adsb_stream_acquire(adsb_ctx *ctx, void **host_buf, size_t *cap_items)
 
 int adsb_stream_commit(adsb_ctx *ctx, size_t n_items)
 {
+    ADSB_RANGE("adsb_stream_commit");
     if (!ctx) return ADSB_E_INVAL;
     auto &S = ctx->st;
     if (!S.open || S.flushed) return fail(ctx, ADSB_E_INVAL, "no open stream");
@@ -1511,6 +1529,7 @@ int adsb_stream_push(adsb_ctx *ctx, const void *samples, size_t n_items)
 
 int adsb_stream_flush(adsb_ctx *ctx)
 {
+    ADSB_RANGE("adsb_stream_flush");
     if (!ctx) return ADSB_E_INVAL;
     auto &S = ctx->st;
     if (!S.open) return fail(ctx, ADSB_E_INVAL, "no open stream");
@@ -1556,6 +1575,7 @@ int adsb_stream_stats(const adsb_ctx *ctx, uint64_t *items, uint64_t *chunks_don
 
 int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, size_t cap, size_t *n_hits)
 {
+    ADSB_RANGE("adsb_burst_finish");
     if (!ctx || !ctx->last.pending) return ADSB_E_INVAL;
     ON_DEVICE(ctx);
     cudaStream_t s = ctx->last.stream;
@@ -1608,6 +1628,7 @@ int adsb_burst_finish(adsb_ctx *ctx, adsb_counters *counters, adsb_hit *hits, si
 int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size_t lead, size_t n_out,
                     float threshold, int64_t base, adsb_hit *hits, size_t cap, size_t *n_hits)
 {
+    ADSB_RANGE("adsb_burst_work");
     if (!ctx || !in || is_c64 < 0 || is_c64 >= kNumFmt) return ADSB_E_INVAL;
     int rc = check_geometry(ctx, n_in, lead, n_out, 0);
     if (rc) return rc;
@@ -1709,6 +1730,7 @@ int adsb_burst_mag_out(adsb_ctx *ctx, float *out, size_t n_out)
 int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out, float threshold,
                      int64_t *hit_idx, float *hit_snr, size_t cap, size_t *n_hits)
 {
+    ADSB_RANGE("adsb_framer_work");
     if (!ctx || !in0 || !n_hits) return ADSB_E_INVAL;
     *n_hits = 0;
     int rc = check_geometry(ctx, n_in, 0, n_out, 0);
@@ -1778,6 +1800,7 @@ int adsb_framer_work(adsb_ctx *ctx, const float *in0, size_t n_in, size_t n_out,
 int adsb_demod_work(adsb_ctx *ctx, const float *in0, size_t n, const int64_t *sob_idx, size_t n_tags,
                     uint8_t *bits, uint8_t *valid)
 {
+    ADSB_RANGE("adsb_demod_work");
     if (!ctx) return ADSB_E_INVAL;
     if (n_tags == 0) return ADSB_OK;             // the common work() call: nothing tagged, nothing to do
     if (!in0 || !sob_idx || !bits || !valid) return ADSB_E_INVAL;

@@ -374,7 +374,9 @@ __global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, Shard
     }
     __syncthreads();
     // (A) the outcome of the previous exchange, looked at before this rank publishes again
-    if (do_prev_check && round == 0 && s_k > s_chk) carry_check(h, own, world, rank, blank, s_k, &s_bad);
+    const unsigned long long x0 = s_k, c0 = s_chk;
+    if (do_prev_check && round == 0 && x0 > c0) carry_check(h, own, world, rank, blank, x0, &s_bad);
+    __syncthreads();            // every thread has read the cells thread 0 rewrites next
     // (B) publish; every rank runs the same sequence of exchanges, so the counters agree without being communicated
     if (t == 0) {
         unsigned long long x = own->xchg;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, Shard
         s_bad = 0;
     }
     __syncthreads();
-    const unsigned long long k = s_k;
+    const unsigned long long k = s_k, chk = s_chk;
     if (do_export && t < world) {
         long long *dst = peers.p[t]->slot[round][rank];
         volatile long long *vd = dst;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(kMaxWorld) shard_carry_kernel(Header *h, Shard
     if (!do_plan) return;
     if (round == 1) {
         // (C1) explicit check of this exchange (end of a run, tests)
-        if (k > s_chk) carry_check(h, own, world, rank, blank, k, &s_bad);
+        if (k > chk) carry_check(h, own, world, rank, blank, k, &s_bad);
         if (t == 0) h->carry_need = 0;
         return;
     }
