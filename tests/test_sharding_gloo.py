@@ -97,3 +97,64 @@ def test_carry_plan_cascade():
     infos = [(10, 1000, N), (1050, N, 1126), (1100, 1500, 1126)]
     e_in, need = sharding.carry_plan(infos, blank)
     assert need == [False, False, False]
+
+
+# ---- peer mode (adsb_shard_*): host-side plumbing under gloo ------------------------------------------------------
+class _FakeCtx(object):
+    """Stands in for gr_adsb_b200.Context where there is no GPU: records what peer_attach asks of it."""
+
+    def __init__(self, rank):
+        self.rank = rank
+        self.attached = None
+
+    def shard_alloc(self, nbytes):
+        return 0x10000 * (self.rank + 1), bytes([self.rank]) * 64          # (sample pointer, 64-byte IPC handle)
+
+    def shard_attach(self, rank, world, handles):
+        self.attached = (rank, world, list(handles))
+
+    def shard_attach_ptrs(self, rank, world, ptrs):
+        self.attached = (rank, world, list(ptrs))
+
+
+def _peer_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = _FakeCtx(rank)
+        ptr = sharding.peer_attach(ctx, dist, rank, world, 1 << 20)
+        out.put((rank, ptr, ctx.attached))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_peer_attach_exchanges_every_handle():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ptr, attached in res:
+        assert ptr == 0x10000 * (rank + 1)
+        assert attached == (rank, world, [bytes([0]) * 64, bytes([1]) * 64])      # every rank's handle, rank order
+
+
+def test_peer_windows_tile_the_whole_buffer_call():
+    """adsb_shard_step's ownership: the ranks' fall ranges tile [0, n_out) of the single whole-stream call exactly
+    (n_out = stream length; the last 8*sps-1 items are look-ahead only, framer.py:72-77)."""
+    for sps in (2, 4, 8):
+        for world in (1, 2, 3, 8):
+            L = 1 << 16
+            prev = 0
+            for r in range(world):
+                lo, hi = sharding.peer_window(r, world, L, sps)
+                assert lo == prev and hi > lo
+                prev = hi
+            assert prev == world * L                    # == n_out of one work() call over world*L items of stream
