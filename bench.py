@@ -751,6 +751,7 @@ def main():
             torch.cuda.synchronize()
             hits = np.zeros(L // (63 * SPS) + 2, g.HIT_DTYPE)
             n_e2e = 0
+            pageable = None
             hbytes = L * item_bytes
             if world == 1:
                 ectx = g.Context(SPS, L, device=local)
@@ -760,6 +761,18 @@ def main():
                     ectx.reset_state()
                     n_e2e = ectx.burst_work_ptr(host.data_ptr(), fmt, L, L, 8 * SPS - 1, THRESHOLD, 0, hits)
                 dt = (time.perf_counter() - t0) / args.e2e_steps
+                # the same call from PAGEABLE memory (what np.fromfile or a GNU Radio buffer is): staged by the library
+                # through its own pinned ring
+                pg = np.empty(host.shape, dtype=host.numpy().dtype)
+                pg[...] = host.numpy()
+                pageable = None
+                for i in range(3):
+                    t1 = time.perf_counter()
+                    ectx.reset_state()
+                    n_pg = ectx.burst_work_ptr(pg.ctypes.data, fmt, L, L, 8 * SPS - 1, THRESHOLD, 0, hits)
+                    pageable = {"value": L / (time.perf_counter() - t1) / 1e6, "unit": "Msamples/s",
+                                "same_hits": bool(n_pg == n_e2e)}
+                del pg
                 ectx.close()
                 api = "adsb_burst_work (pinned host %s in, adsb_hit[] out)" % fmt_name
             else:
@@ -810,6 +823,8 @@ def main():
             line["e2e"] = {"value": world * L / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": world * hbytes,
                            "d2h_bytes_per_step": int(ne.item()) * 32 + 96 * world, "steps": args.e2e_steps,
                            "ms_per_step": dt * 1e3, "hits_per_step": int(ne.item()), "api": api}
+            if world == 1 and pageable is not None:
+                line["e2e"]["from_pageable_memory"] = pageable
             del host
         except Exception as e:           # pragma: no cover
             line["e2e"] = {"error": repr(e)}

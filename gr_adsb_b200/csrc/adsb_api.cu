@@ -176,6 +176,8 @@ struct adsb_ctx {
         size_t out_n, out_cap, out_read;
         unsigned long long n_cand, n_crc, n_demod;
     } st;
+    void *h_ring[2];             // adsb_burst_work from pageable memory: pinned staging, one H2D chunk each
+    cudaEvent_t ev_ring[2];
     Rec *h_tmp;                  // host scratch of the two-block entry points
     size_t h_tmp_cap;
     unsigned char *h_bits;
@@ -770,6 +772,10 @@ void adsb_destroy(adsb_ctx *ctx)
     cudaFree(ctx->d_mag);
     adsb_stream_close(ctx);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
+        if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
+    }
     if (ctx->small.out) cudaFreeHost(ctx->small.out);
     if (ctx->small.in) cudaFreeHost(ctx->small.in);
     if (ctx->small.mag) cudaFreeHost(ctx->small.mag);
@@ -1298,13 +1304,13 @@ namespace {
 void big_memcpy(void *dst, const void *src, size_t bytes)
 {
 #if !defined(ADSB_HOST_EMU)
-    constexpr size_t kPart = 8u << 20;
+    constexpr size_t kPart = 4u << 20;
     unsigned hw = std::thread::hardware_concurrency();
     size_t parts = bytes / kPart;
-    if (parts > 8) parts = 8;
+    if (parts > 16) parts = 16;
     if (hw && parts > hw) parts = hw;
     if (parts >= 2) {
-        std::thread th[8];
+        std::thread th[16];
         const size_t per = (bytes / parts + 63) & ~(size_t)63;
         size_t off = 0;
         unsigned n = 0;
@@ -1662,9 +1668,37 @@ int adsb_burst_work(adsb_ctx *ctx, const void *in, int is_c64, size_t n_in, size
     size_t copied = 0;
     long long tiles_done = 0;
     int ring = 0;
+    // A pageable source (np.fromfile, GNU Radio buffers ...) would make every cudaMemcpyAsync a synchronous, staged copy:
+    // stage it ourselves through two pinned chunk buffers, a few host threads copying chunk i+1 while chunk i crosses PCIe.
+    bool pageable = true;
+#if !defined(ADSB_HOST_EMU)
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, in) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+#endif
+    if (pageable) {
+        for (int i = 0; i < 2; i++) {
+            if (!ctx->h_ring[i]) {
+                cudaError_t e = cudaHostAlloc(&ctx->h_ring[i], kPipeChunk * 8, cudaHostAllocMapped);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming);
+                if (e != cudaSuccess) return fail(ctx, ADSB_E_NOMEM, "pinned staging ring", e);
+            }
+        }
+    }
+    int hb = 0;
     while (copied < n_in) {
         const size_t n = (n_in - copied < kPipeChunk) ? (n_in - copied) : kPipeChunk;
-        CK(cudaMemcpyAsync(dst + copied * isz, src + copied * isz, n * isz, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (pageable) {
+            CK(cudaEventSynchronize(ctx->ev_ring[hb]));          // the copy that last used this staging buffer has left it
+            big_memcpy(ctx->h_ring[hb], src + copied * isz, n * isz);
+            CK(cudaMemcpyAsync(dst + copied * isz, ctx->h_ring[hb], n * isz, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_ring[hb], ctx->copy_stream));
+            hb ^= 1;
+        } else {
+            CK(cudaMemcpyAsync(dst + copied * isz, src + copied * isz, n * isz, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
         copied += n;
         long long ready = (copied == n_in) ? n_tiles : ((long long)copied - ctx->rh) / ctx->T;
         if (ready > n_tiles) ready = n_tiles;
