@@ -18,6 +18,10 @@ namespace adsb {
 #ifndef ADSB_MIN_CTAS_BIG
 #define ADSB_MIN_CTAS_BIG 4  // same for the 8192-sample tile kernels (8 Msps and unspecialised rates)
 #endif
+#ifndef ADSB_CW
+#define ADSB_CW 20            // samples per detect chunk at 2 / 4 samples per symbol: with 20 the float4 loads of the dense pre-filter
+#endif                        // (thread stride 80 B) fall into 8 different 16-byte bank groups per quarter-warp; with 16 (stride 64 B)
+                              // they are 4-way bank conflicted -- 40 % of the kernel's shared-memory wavefronts (ncu, round 2)
 #ifndef ADSB_LMAX2
 #define ADSB_LMAX2 8          // longest run resolved bit-parallel at 2 samples/symbol (8 otherwise)
 #endif
@@ -27,7 +31,9 @@ namespace adsb {
 // owns one 16-sample chunk of the tile (two at 8 Msps and unspecialised rates), so the tile grows with the CTA.
 template <int SPS, int NT = kThreads>
 struct Geo {
-    static constexpr int T = ((SPS == 2 || SPS == 4) ? 16 : 32) * NT;
+    static constexpr int CW = (SPS == 2 || SPS == 4) ? ADSB_CW : 16;  // samples per detect chunk (one thread, one 32-bit window)
+    static constexpr int LB = 32 - CW;                                // look-back bits of the window below the chunk
+    static constexpr int T = ((SPS == 2 || SPS == 4) ? CW : 32) * NT;
     static constexpr int H = SPS / 2;                                  // 0: run-time
     // right halo: >= 120*SPS and such that the staged span is a multiple of NT (384 / 640 / 1152 for NT = 256)
     static constexpr int RH = SPS == 0 ? 0 : ((120 * SPS + kLeftHalo + NT - 1) / NT) * NT - kLeftHalo;
@@ -35,11 +41,13 @@ struct Geo {
     static constexpr int NPT = S / NT;                                 // slots per thread in phase 1
     static constexpr int LMAX = ADSB_LMAX2 > 0 && SPS == 2 ? ADSB_LMAX2 : 8;   // run lengths resolved bit-parallel
     static constexpr int DB = LMAX / 2;                                // how far a centre lies before its chunk
-    static constexpr int NV = (14 + 5 * H + 4 + 1 + 3) / 4;            // float4 loads of the dense pre-filter
+    static constexpr int NV = (CW + 3 + 5 * H + 3) / 4;                // float4 loads of the dense pre-filter
     static_assert(SPS == 0 || (S % NT == 0 && RH >= 120 * SPS && RH % 32 == 0), "tile geometry");
+    static_assert(CW % 4 == 0 && LB >= LMAX + 1 && T % 32 == 0, "chunk geometry");
 };
 
-__host__ __device__ inline int tile_items(int sps, int nt = kThreads) { return ((sps == 2 || sps == 4) ? 16 : 32) * nt; }
+__host__ __device__ inline int tile_items(int sps, int nt = kThreads) { return ((sps == 2 || sps == 4) ? ADSB_CW : 32) * nt; }
+__host__ __device__ inline int chunk_width(int sps) { return (sps == 2 || sps == 4) ? ADSB_CW : 16; }
 __host__ __device__ inline int right_halo(int sps, int nt = kThreads)
 {
     if (sps == 2 || sps == 4 || sps == 8) return ((120 * sps + kLeftHalo + nt - 1) / nt) * nt - kLeftHalo;
@@ -47,7 +55,8 @@ __host__ __device__ inline int right_halo(int sps, int nt = kThreads)
 }
 
 #ifndef ADSB_MIN_CTAS
-#define ADSB_MIN_CTAS 8      // resident CTAs per SM the 4096-sample tile kernels are compiled for
+#define ADSB_MIN_CTAS (ADSB_CW == 16 ? 8 : 7)   // resident CTAs per SM of the 2 / 4 samples-per-symbol kernels: 8 x 24.3 KB
+                                                // (4096-sample tiles) or 7 x 31 KB (5120-sample tiles) of shared memory
 #endif
 constexpr int kTileSlots = 32;    // candidate records reserved per tile (typical busy tile: 5-10)
 constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
@@ -57,8 +66,8 @@ struct TileSmem {
     float *mag;             // S
     unsigned *bits;         // S/32
     unsigned short *list;   // T/2 + 2
-    unsigned short *xmask;  // T/16   extra candidate bits (by fall position) from the long-run pass
-    unsigned short *xlong;  // T/16   which of them are long-run entries
+    unsigned *xmask;        // T/CW   extra candidate bits (by fall position) from the long-run pass
+    unsigned *xlong;        // T/CW   which of them are long-run entries
     unsigned short *slow;   // kSlowCap fall slots
     int *scratch;           // scratch_ints(NW): slots below + per-warp reduction cells
 };
@@ -71,9 +80,9 @@ __host__ __device__ inline size_t tile_smem_bytes(int T, int rh, int nw = kWarps
 {
     size_t S = (size_t)kLeftHalo + T + rh;
     size_t b = S * 4;
-    b += align16((S / 32) * 4);
+    b += align16((S / 32 + 1) * 4);
     b += align16(((size_t)T / 2 + 2) * 2);
-    b += align16((size_t)(T / 16) * 2) * 2;
+    b += align16((size_t)(T / 16) * 4) * 2;
     b += align16((size_t)kSlowCap * 2);
     b += (size_t)scratch_ints(nw) * 4;
     return b;
@@ -86,13 +95,13 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
     s.mag = reinterpret_cast<float *>(raw);
     raw += S * 4;
     s.bits = reinterpret_cast<unsigned *>(raw);
-    raw += align16((S / 32) * 4);
+    raw += align16((S / 32 + 1) * 4);
     s.list = reinterpret_cast<unsigned short *>(raw);
     raw += align16(((size_t)T / 2 + 2) * 2);
-    s.xmask = reinterpret_cast<unsigned short *>(raw);
-    raw += align16((size_t)(T / 16) * 2);
-    s.xlong = reinterpret_cast<unsigned short *>(raw);
-    raw += align16((size_t)(T / 16) * 2);
+    s.xmask = reinterpret_cast<unsigned *>(raw);
+    raw += align16((size_t)(T / 16) * 4);
+    s.xlong = reinterpret_cast<unsigned *>(raw);
+    raw += align16((size_t)(T / 16) * 4);
     s.slow = reinterpret_cast<unsigned short *>(raw);
     raw += align16((size_t)kSlowCap * 2);
     s.scratch = reinterpret_cast<int *>(raw);
@@ -396,6 +405,20 @@ __device__ __forceinline__ void slice_pair_bits(const ScanParams &P, const float
     }
 }
 
+// The 32-bit window of detect chunk c: its CW samples in bits LB..31, the LB samples before it in bits 0..LB-1
+// (LB >= longest bit-parallel run + 1).  k0 = slot of the chunk's first sample.
+template <int CW>
+__device__ __forceinline__ unsigned chunk_window(const unsigned *bits, int k0)
+{
+    constexpr int LB = 32 - CW;
+    const int s0 = k0 - LB;                       // slot of window bit 0
+    if (CW == 16) {                               // s0 is a multiple of 16: one or two aligned words
+        const unsigned cur = bits[k0 >> 5], prev = bits[(k0 >> 5) - 1];
+        return (k0 & 16) ? cur : __funnelshift_l(prev, cur, 16);
+    }
+    return __funnelshift_r(bits[s0 >> 5], bits[(s0 >> 5) + 1], s0 & 31);
+}
+
 // ---- phases 1 + 2 of one tile, by the 256 scan threads (threads 0..255 of the CTA) --------------------------
 // On return (after the caller's next group barrier) sm.list, scratch[kScrNCand|kScrOff|kScrFast] are valid.
 // UG: loads an edge tile keeps in flight per thread (the latency-path kernel, which runs alone on its SM and has the
@@ -553,9 +576,11 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     gb.sync();
 
     // ---- phase 2: falls -> pulse centres -> preamble match ----
-    // Each thread owns the falls of 16-sample chunks; W holds the chunk in bits 16..31 and the 16 samples
-    // before it in bits 0..15.  cmask: candidates keyed by the bit of their FALL inside the chunk.
-    constexpr int NCH = (T / 16 + NT - 1) / NT;
+    // Each thread owns the falls of CW-sample chunks; W holds the chunk in bits LB..31 and the LB samples
+    // before it in bits 0..LB-1.  cmask: candidates keyed by the bit of their FALL inside the chunk.
+    constexpr int CW = G::CW, LB = G::LB;
+    constexpr unsigned kChunkBits = 0xffffffffu << LB;
+    constexpr int NCH = (T / CW + NT - 1) / NT;
     unsigned cmask[NCH], lmask[NCH];
     int cent[NCH];              // centre slot of the candidate found last in this thread's chunk (valid when it has exactly one)
     int tmax = -1;              // largest centre (shared-memory slot) of a complete short pulse
@@ -567,13 +592,11 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         cmask[ci] = 0;
         lmask[ci] = 0;
         cent[ci] = 0;
-        if (c >= T / 16) continue;
-        const int wq = kLeftHalo / 32 + (c >> 1);
-        const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
-        const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
-        unsigned F = ~W & (W << 1) & 0xffff0000u;
-        unsigned R = W & ~(W << 1) & 0xffff0000u;
-        const int k0 = kLeftHalo + c * 16;       // slot of chunk bit 0 (= W bit 16)
+        if (c >= T / CW) continue;
+        const int k0 = kLeftHalo + c * CW;       // slot of chunk bit 0 (= W bit LB)
+        const unsigned W = chunk_window<CW>(sm.bits, k0);
+        unsigned F = ~W & (W << 1) & kChunkBits;
+        unsigned R = W & ~(W << 1) & kChunkBits;
         unsigned cm = 0, longf = 0, lm = 0;
         if (fast) {
             if (R) tflags |= kFlagRise;
@@ -588,12 +611,12 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             }
             // runs longer than LMAX: walk the staged bitmap in-thread; only runs that leave the staged
             // span are deferred to the warp-cooperative path
-            unsigned lf = acc >> 16;
+            unsigned lf = acc >> LB;
             while (lf) {
                 const int b = __ffs(lf) - 1;
                 lf &= lf - 1;
                 const int kf = k0 + b;
-                const int pos = 16 + b;
+                const int pos = LB + b;
                 const int run = __clz(~(W << (32 - pos)));      // ones below the fall inside W
                 int r = kf - run;
                 if (run >= pos) {                               // run leaves W: walk the staged bitmap
@@ -612,7 +635,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 }
             }
             if (C) {
-                tmax = max(tmax, k0 + (31 - __clz(C)) - 16);
+                tmax = max(tmax, k0 + (31 - __clz(C)) - LB);
                 // dense pre-filter: taps 3,4,5 must not exceed half the centre sample (framer.py:141,50)
                 float vals[G::NV * 4];
 #pragma unroll
@@ -628,33 +651,33 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     // NaN.  One FADD (FMA pipe) and one funnel shift replace FSETP + SEL + ADD, all three on the ALU pipe
                     // this kernel loads most.  (float32 input may hold -0.0 or negative values: compare as before.)
 #pragma unroll
-                    for (int j = 14 + G::DB; j >= 0; j--) {
+                    for (int j = CW - 2 + G::DB; j >= 0; j--) {
                         const int i0 = 4 - G::DB + j;
                         const float half = __fmul_rn(vals[i0], 0.5f);
                         const float m3 = fmaxf(fmaxf(vals[i0 + 3 * G::H], vals[i0 + 4 * G::H]), vals[i0 + 5 * G::H]);
                         Q = __funnelshift_l(gt_sign(m3, half), Q, 1);        // Q = Q << 1 | (m3 > half)
                     }
-                    Q = ~Q << (16 - G::DB);               // bit 16 - DB + j <-> position j (bit 31 is junk; C never has it)
+                    Q = ~Q << (LB - G::DB);               // bit LB - DB + j <-> position j (bit 31 is junk; C never has it)
                 } else
                 {
 #pragma unroll
-                    for (int j = 0; j < 15 + G::DB; j++) {
+                    for (int j = 0; j < CW - 1 + G::DB; j++) {
                         const int i0 = 4 - G::DB + j;                 // index of position k0 - DB + j in vals
                         const float half = __fmul_rn(vals[i0], 0.5f);
                         // none of the three taps may exceed half (NaN taps count as low, like `tap > half`)
                         const float m3 = fmaxf(fmaxf(vals[i0 + 3 * G::H], vals[i0 + 4 * G::H]), vals[i0 + 5 * G::H]);
-                        Q |= !(m3 > half) ? (1u << (16 - G::DB + j)) : 0u;
+                        Q |= !(m3 > half) ? (1u << (LB - G::DB + j)) : 0u;
                     }
                 }
                 unsigned Tm = C & Q;
                 while (Tm) {
                     const int pc = 31 - __clz(Tm);
                     Tm &= ~(1u << pc);
-                    if (preamble_match_rest<G::H>(sm.mag + k0 + pc - 16)) {
+                    if (preamble_match_rest<G::H>(sm.mag + k0 + pc - LB)) {
                         // key the candidate by its fall: first zero above the centre
                         const int fb = pc + __ffs(~(W >> (pc + 1)));
-                        cm |= 1u << (fb - 16);
-                        cent[ci] = k0 + pc - 16;
+                        cm |= 1u << (fb - LB);
+                        cent[ci] = k0 + pc - LB;
                     }
                 }
             }
@@ -662,18 +685,18 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
             // generic per-edge path (window edges, halo'd shards, unspecialised sample rates)
             const long long i0 = w0 + k0;
             long long lo = P.own_lo - i0, hi = P.own_hi - i0;
-            lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
-            hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
-            const unsigned own = (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << 16) : 0u;
+            lo = lo < 0 ? 0 : (lo > CW ? CW : lo);
+            hi = hi < 0 ? 0 : (hi > CW ? CW : hi);
+            const unsigned own = (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << LB) : 0u;
             F &= own;
             R &= own;
             if (R) tflags |= kFlagRise;
             if (F) tflags |= kFlagFall;
-            unsigned fm = F >> 16;
+            unsigned fm = F >> LB;
             while (fm) {
                 const int b = __ffs(fm) - 1;
                 fm &= fm - 1;
-                const int pos = 16 + b;                         // bit of the fall in W
+                const int pos = LB + b;                         // bit of the fall in W
                 const int run = __clz(~(W << (32 - pos)));      // ones just below it (pos if all of them)
                 if (run >= pos) {
                     longf |= 1u << b;
@@ -729,7 +752,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
     // ---- long runs (rare): one warp per deferred fall ----
     long long &s_max_long = *reinterpret_cast<long long *>(sm.scratch + scr_max_long(NW));
     if (gb.sync_or(have_long)) {
-        for (int c = tid; c < T / 16; c += NT) {
+        for (int c = tid; c < T / CW; c += NT) {
             sm.xmask[c] = 0;
             sm.xlong[c] = 0;
         }
@@ -746,30 +769,28 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 if (lane == 0) {
                     atomicMax(&s_max_long, p);
                     if (m) {
-                        const int c = (kf - kLeftHalo) >> 4, b = (kf - kLeftHalo) & 15;
-                        atomicOr(reinterpret_cast<unsigned *>(sm.xmask) + (c >> 1), (1u << b) << ((c & 1) * 16));
-                        atomicOr(reinterpret_cast<unsigned *>(sm.xlong) + (c >> 1), (1u << b) << ((c & 1) * 16));
+                        const int c = (kf - kLeftHalo) / CW, b = (kf - kLeftHalo) % CW;
+                        atomicOr(sm.xmask + c, 1u << b);
+                        atomicOr(sm.xlong + c, 1u << b);
                     }
                 }
             }
         } else {
             // more long runs than the deferral list holds: every warp rescans its own chunks
-            for (int c = wid; c < T / 16; c += NW) {
-                const int wq = kLeftHalo / 32 + (c >> 1);
-                const unsigned cur = sm.bits[wq], prev = sm.bits[wq - 1];
-                const unsigned W = (c & 1) ? cur : __funnelshift_l(prev, cur, 16);
-                unsigned F = ~W & (W << 1) & 0xffff0000u;
-                const int k0 = kLeftHalo + c * 16;
+            for (int c = wid; c < T / CW; c += NW) {
+                const int k0 = kLeftHalo + c * CW;
+                const unsigned W = chunk_window<CW>(sm.bits, k0);
+                unsigned F = ~W & (W << 1) & kChunkBits;
                 const long long i0 = w0 + k0;
                 long long lo = P.own_lo - i0, hi = P.own_hi - i0;
-                lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
-                hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
-                F &= (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << 16) : 0u;
-                unsigned fm = F >> 16;
+                lo = lo < 0 ? 0 : (lo > CW ? CW : lo);
+                hi = hi < 0 ? 0 : (hi > CW ? CW : hi);
+                F &= (hi > lo) ? ((((1u << hi) - 1u) & ~((1u << lo) - 1u)) << LB) : 0u;
+                unsigned fm = F >> LB;
                 while (fm) {
                     const int b = __ffs(fm) - 1;
                     fm &= fm - 1;
-                    const int pos = 16 + b;
+                    const int pos = LB + b;
                     const int run = __clz(~(W << (32 - pos)));
                     if (fast ? (run <= G::LMAX) : (run < pos)) continue;     // handled as a short run already
                     long long p;
@@ -778,8 +799,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                     if (lane == 0) {
                         atomicMax(&s_max_long, p);
                         if (m) {
-                            atomicOr(reinterpret_cast<unsigned *>(sm.xmask) + (c >> 1), (1u << b) << ((c & 1) * 16));
-                            atomicOr(reinterpret_cast<unsigned *>(sm.xlong) + (c >> 1), (1u << b) << ((c & 1) * 16));
+                            atomicOr(sm.xmask + c, 1u << b);
+                            atomicOr(sm.xlong + c, 1u << b);
                         }
                     }
                 }
@@ -789,7 +810,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
 #pragma unroll
         for (int ci = 0; ci < NCH; ci++) {
             const int c = tid + ci * NT;
-            if (c < T / 16) {
+            if (c < T / CW) {
                 cmask[ci] |= sm.xmask[c];
                 lmask[ci] |= sm.xlong[c];
             }
@@ -833,7 +854,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
                 }
                 int off = base + before + excl;
                 unsigned cm = cmask[ci];
-                const int k0 = kLeftHalo + (tid + ci * NT) * 16;
+                const int k0 = kLeftHalo + (tid + ci * NT) * CW;
                 if (cnt == 1 && lmask[ci] == 0) {
                     sm.list[off] = (unsigned short)cent[ci];        // centre kept since detection
                     cm = 0;
@@ -955,7 +976,7 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
 
 // ---- the kernel: one CTA (8 warps) per tile, phases in sequence ---------------------------------------------
 template <int SPS, int FMT, int NT = kThreads>
-__global__ void __launch_bounds__(NT, ((Geo<SPS, NT>::T <= 16 * NT) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) * kThreads / NT)
+__global__ void __launch_bounds__(NT, ((SPS == 2 || SPS == 4) ? ADSB_MIN_CTAS : ADSB_MIN_CTAS_BIG) * kThreads / NT)
 scan_slice_kernel(const ScanParams P)
 {
 #if defined(ADSB_HOST_EMU)

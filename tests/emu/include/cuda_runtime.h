@@ -147,6 +147,11 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)((v << (shift & 31)) >> 32);
 }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
+{
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)(v >> (shift & 31));
+}
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }

@@ -30,6 +30,7 @@ def _defs(*on):
 
 VARIANTS = {
     "default": _defs(),
+    "cw16": _defs() + ["-DADSB_CW=16"],     # 16-sample detect chunks (round-1 geometry: bank-conflicted pre-filter loads)
     # latency path with %globaltimer stamps per phase (tools/latency_probe.py prints them)
     "timing": _defs() + ["-DADSB_SMALL_TIMING=1"],
 }
