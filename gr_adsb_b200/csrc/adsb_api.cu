@@ -297,7 +297,7 @@ void crc_table(unsigned *t)
 template <int SPS, int FMT, int NT>
 cudaError_t launch_scan_t(const ScanParams &P, unsigned n_blocks, cudaStream_t s, bool *configured)
 {
-    const size_t smem = tile_smem_bytes(Geo<SPS, NT>::T, P.rh, NT / 32);
+    const size_t smem = tile_smem_bytes(Geo<SPS, NT>::T, P.rh, Geo<SPS, NT>::CW, NT / 32);
     if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(scan_slice_kernel<SPS, FMT, NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -525,7 +525,7 @@ double host_now()
 template <int SPS, int FMT>
 cudaError_t launch_small_t(const ScanParams &P, const SmallParams &Q, cudaStream_t s, bool *configured)
 {
-    const size_t smem = tile_smem_bytes(Geo<SPS, kThreads>::T, P.rh, kWarps);
+    const size_t smem = tile_smem_bytes(Geo<SPS, kThreads>::T, P.rh, Geo<SPS, kThreads>::CW, kWarps);
     if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(small_work_kernel<SPS, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

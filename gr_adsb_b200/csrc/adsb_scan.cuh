@@ -15,8 +15,14 @@
 
 namespace adsb {
 
+#ifndef ADSB_NCH2
+#define ADSB_NCH2 1           // detect chunks per thread at 2 / 4 samples per symbol (tile = ADSB_NCH2 * ADSB_CW * 256 samples)
+#endif
+#ifndef ADSB_CW8
+#define ADSB_CW8 12           // samples per detect chunk of the other kernels (8 Msps, unspecialised rates): two chunks per thread
+#endif
 #ifndef ADSB_MIN_CTAS_BIG
-#define ADSB_MIN_CTAS_BIG 4  // same for the 8192-sample tile kernels (8 Msps and unspecialised rates)
+#define ADSB_MIN_CTAS_BIG (ADSB_CW8 == 16 ? 4 : ADSB_CW8 == 12 ? 5 : 3)  // resident CTAs per SM of those kernels
 #endif
 #ifndef ADSB_CW
 #define ADSB_CW 20            // samples per detect chunk at 2 / 4 samples per symbol: with 20 the float4 loads of the dense pre-filter
@@ -31,9 +37,9 @@ namespace adsb {
 // owns one 16-sample chunk of the tile (two at 8 Msps and unspecialised rates), so the tile grows with the CTA.
 template <int SPS, int NT = kThreads>
 struct Geo {
-    static constexpr int CW = (SPS == 2 || SPS == 4) ? ADSB_CW : 16;  // samples per detect chunk (one thread, one 32-bit window)
+    static constexpr int CW = (SPS == 2 || SPS == 4) ? ADSB_CW : ADSB_CW8;  // samples per detect chunk (one 32-bit window)
     static constexpr int LB = 32 - CW;                                // look-back bits of the window below the chunk
-    static constexpr int T = ((SPS == 2 || SPS == 4) ? CW : 32) * NT;
+    static constexpr int T = ((SPS == 2 || SPS == 4) ? ADSB_NCH2 * CW : 2 * CW) * NT;
     static constexpr int H = SPS / 2;                                  // 0: run-time
     // right halo: >= 120*SPS and such that the staged span is a multiple of NT (384 / 640 / 1152 for NT = 256)
     static constexpr int RH = SPS == 0 ? 0 : ((120 * SPS + kLeftHalo + NT - 1) / NT) * NT - kLeftHalo;
@@ -43,11 +49,10 @@ struct Geo {
     static constexpr int DB = LMAX / 2;                                // how far a centre lies before its chunk
     static constexpr int NV = (CW + 3 + 5 * H + 3) / 4;                // float4 loads of the dense pre-filter
     static_assert(SPS == 0 || (S % NT == 0 && RH >= 120 * SPS && RH % 32 == 0), "tile geometry");
-    static_assert(CW % 4 == 0 && LB >= LMAX + 1 && T % 32 == 0, "chunk geometry");
+    static_assert(CW % 4 == 0 && CW >= 12 && LB >= LMAX + 1 && T % 32 == 0, "chunk geometry");
 };
 
-__host__ __device__ inline int tile_items(int sps, int nt = kThreads) { return ((sps == 2 || sps == 4) ? ADSB_CW : 32) * nt; }
-__host__ __device__ inline int chunk_width(int sps) { return (sps == 2 || sps == 4) ? ADSB_CW : 16; }
+__host__ __device__ inline int tile_items(int sps, int nt = kThreads) { return ((sps == 2 || sps == 4) ? ADSB_NCH2 * ADSB_CW : 2 * ADSB_CW8) * nt; }
 __host__ __device__ inline int right_halo(int sps, int nt = kThreads)
 {
     if (sps == 2 || sps == 4 || sps == 8) return ((120 * sps + kLeftHalo + nt - 1) / nt) * nt - kLeftHalo;
@@ -76,19 +81,19 @@ __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t
 
 __host__ __device__ constexpr int scratch_ints(int nw) { return 32 + 4 * nw; }      // 64 for the 8-warp CTA
 
-__host__ __device__ inline size_t tile_smem_bytes(int T, int rh, int nw = kWarps)
+__host__ __device__ inline size_t tile_smem_bytes(int T, int rh, int cw, int nw = kWarps)
 {
     size_t S = (size_t)kLeftHalo + T + rh;
     size_t b = S * 4;
     b += align16((S / 32 + 1) * 4);
     b += align16(((size_t)T / 2 + 2) * 2);
-    b += align16((size_t)(T / 16) * 4) * 2;
+    b += align16((size_t)(T / cw) * 4) * 2;      // one word per detect chunk
     b += align16((size_t)kSlowCap * 2);
     b += (size_t)scratch_ints(nw) * 4;
     return b;
 }
 
-__device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
+__device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh, int cw)
 {
     TileSmem s;
     const size_t S = (size_t)kLeftHalo + T + rh;
@@ -99,9 +104,9 @@ __device__ __forceinline__ TileSmem carve(unsigned char *raw, int T, int rh)
     s.list = reinterpret_cast<unsigned short *>(raw);
     raw += align16(((size_t)T / 2 + 2) * 2);
     s.xmask = reinterpret_cast<unsigned *>(raw);
-    raw += align16((size_t)(T / 16) * 4);
+    raw += align16((size_t)(T / cw) * 4);
     s.xlong = reinterpret_cast<unsigned *>(raw);
-    raw += align16((size_t)(T / 16) * 4);
+    raw += align16((size_t)(T / cw) * 4);
     s.slow = reinterpret_cast<unsigned short *>(raw);
     raw += align16((size_t)kSlowCap * 2);
     s.scratch = reinterpret_cast<int *>(raw);
@@ -984,7 +989,7 @@ scan_slice_kernel(const ScanParams P)
 #else
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
-    const TileSmem sm = carve(smem_raw, Geo<SPS, NT>::T, SPS ? Geo<SPS, NT>::RH : P.rh);
+    const TileSmem sm = carve(smem_raw, Geo<SPS, NT>::T, SPS ? Geo<SPS, NT>::RH : P.rh, Geo<SPS, NT>::CW);
     // CTA 1 <-> the CTA of the launch's final tile (ScanParams::early_tile); all in 32-bit uniform arithmetic
     unsigned bx = blockIdx.x;
     const unsigned eb = P.early_tile;

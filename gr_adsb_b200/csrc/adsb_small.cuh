@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) small_work_kernel(const ScanParam
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
     using G = Geo<SPS, kThreads>;
-    const TileSmem sm = carve(smem_raw, G::T, SPS ? G::RH : P.rh);
+    const TileSmem sm = carve(smem_raw, G::T, SPS ? G::RH : P.rh, G::CW);
     const long long tile = (long long)P.tile_first + blockIdx.x;
     const int tid = threadIdx.x;
     const CtaBar gb;
