@@ -660,6 +660,14 @@ def main():
         stepper2.load(data)
         stream2 = torch.cuda.Stream(device=dev)
         pipe.append((stepper2, stream2))
+    # The ranks have just idled for seconds (rank 0 ran the oracle of the verification): bring every GPU back to its working
+    # clocks and power state before the W warm-up steps -- a timed region of K x 0.5 ms is otherwise decided by whichever GPU
+    # is still ramping up.  (Kept short: these GPUs run into their power cap under sustained load -- MEASURED_PEAKS.json
+    # records 1372 MHz under load against 1965 MHz boost -- and the ranks' steps are coupled, so one capped GPU sets the pace
+    # of all: 0.67 ms per step was seen once on 4 GPUs and 0.76 ms once on 2, between 0.555-0.566 ms on the same boxes.)
+    for _ in range(100):                    # ~55 ms; the same count on every rank (the ranks' steps are coupled)
+        pipe[0][0].step(pipe[0][1].cuda_stream)
+    sync_all()
     for i in range(args.warmup * len(pipe)):
         st, sm = pipe[i % len(pipe)]
         st.step(sm.cuda_stream)
@@ -685,6 +693,11 @@ def main():
             st.check(sm.cuda_stream)     # the last step's carry check (every other step's rode on its successor)
     sync_all()
     clocks = sampler.stop()
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        clocks["all_ranks"] = {"sm_mhz_min": min((c["sm_mhz"] or 0) for c in allc),
+                               "reasons": sorted(set(r for c in allc for r in c["reasons"]))}
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
