@@ -23,9 +23,9 @@ __device__ __forceinline__ uint4 ld_cg_u4(const uint4 *p)
 #endif
 }
 
-constexpr int kSmallTiles = 64;          // tiles per call on this path (256 Ki samples at 2 / 4 Msps)
+constexpr int kSmallTiles = 64;          // tiles per call on this path (320 Ki samples at 2 / 4 Msps)
 constexpr int kSmallCand = 2048;         // candidates resolved in shared memory; more -> the host runs the resolve kernels
-constexpr int kSmallHits = 2112;         // >= (kSmallTiles * 8192) / (63 * 2) + 2 hit records in the pinned result block
+constexpr int kSmallHits = 2624;         // >= (kSmallTiles * 5120) / (63 * 2) + 2 hit records in the pinned result block (more -> fallback)
 constexpr unsigned kFlagSmallOverflow = 64u;
 
 #ifndef ADSB_SMALL_TIMING

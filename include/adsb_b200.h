@@ -247,7 +247,7 @@ int adsb_stream_flush(adsb_ctx *ctx);
 int adsb_stream_close(adsb_ctx *ctx);
 int adsb_stream_stats(const adsb_ctx *ctx, uint64_t *items, uint64_t *chunks_done, uint64_t *hits, uint64_t *crc_ok);
 
-/* The latency path.  Calls of GNU Radio size (float32 or complex64 input, at most 64 tiles = 256 Ki items at 2 Msps,
+/* The latency path.  Calls of GNU Radio size (float32 or complex64 input, at most 64 tiles = 320 Ki items at 2 Msps,
  * no error correction) do not go through the copy / multi-kernel pipeline: adsb_framer_work, adsb_demod_work and
  * adsb_burst_work stage the caller's (pageable) buffer through pinned, device-mapped memory, launch ONE kernel that
  * scans, slices and resolves the call and writes hits and counters back into pinned memory, and spin on its
