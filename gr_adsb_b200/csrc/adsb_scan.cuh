@@ -34,7 +34,7 @@ namespace adsb {
 
 // ---- compile-time geometry per samples-per-symbol and CTA size -------------------------------------------
 // NT = threads per CTA (256 in the shipped build; 128 / 512 exist for A/B builds, ADSB_SCAN_NT_VARIANTS).  A thread
-// owns one 16-sample chunk of the tile (two at 8 Msps and unspecialised rates), so the tile grows with the CTA.
+// owns one 20-sample chunk of the tile (two 12-sample chunks at 8 Msps and unspecialised rates), so the tile grows with the CTA.
 template <int SPS, int NT = kThreads>
 struct Geo {
     static constexpr int CW = (SPS == 2 || SPS == 4) ? ADSB_CW : ADSB_CW8;  // samples per detect chunk (one 32-bit window)
@@ -427,7 +427,7 @@ __device__ __forceinline__ unsigned chunk_window(const unsigned *bits, int k0)
 // ---- phases 1 + 2 of one tile, by the 256 scan threads (threads 0..255 of the CTA) --------------------------
 // On return (after the caller's next group barrier) sm.list, scratch[kScrNCand|kScrOff|kScrFast] are valid.
 // UG: loads an edge tile keeps in flight per thread (the latency-path kernel, which runs alone on its SM and has the
-// registers, takes a whole 4096-sample tile in one batch: one PCIe round trip instead of three)
+// registers, takes most of a tile in one batch: one or two PCIe round trips instead of four)
 template <int SPS, int FMT, int NT, class GB, int UG = 6>
 __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &sm, const long long tile, const GB gb)
 {
@@ -455,7 +455,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const TileSmem &s
         const long long ta = tile + P.prefetch_tiles;
         if (((unsigned)ta - P.fast_lo) <= P.fast_span) {
             // only that tile's own T samples: its halos are the neighbouring tiles' own ranges, prefetched by the
-            // CTAs that run next to this one; T * itemsize / 128 lines = one per thread for complex64 at T = 4096
+            // CTAs that run next to this one; T * itemsize / 128 lines = 320 for complex64 at T = 5120
             const char *base = reinterpret_cast<const char *>(P.in) + ta * T * item_bytes<FMT>();
             constexpr int kLines = T * item_bytes<FMT>() / 128;
 #if !defined(ADSB_HOST_EMU)
