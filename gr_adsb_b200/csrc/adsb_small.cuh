@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) small_work_kernel(const ScanParam
     unsigned long long tstamp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     ADSB_TSTAMP(0);
-    scan_tile<SPS, FMT, kThreads, CtaBar, 19>(P, sm, tile, gb);
+    scan_tile<SPS, FMT, kThreads, CtaBar, 30>(P, sm, tile, gb);   // 30 rows in flight: a whole tile (22-29 rows) in one batch
     gb.sync();
     ADSB_TSTAMP(2);
     slice_tile<SPS, FMT, kThreads>(P, sm, tile, tid, kWarps, gb);
