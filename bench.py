@@ -384,6 +384,9 @@ def time_kernel(ctx, run_plain, n):
     ctx.profile_enable(True)
     a_, b_ = [], []
     for _ in range(n):
+        # two steps back to back, the events of the second are read: its kernels are already queued when its first event
+        # fires, so the interval is the kernel, not the kernel plus the host's launch latency on an idle stream
+        run_plain()
         run_plain()
         a, b = ctx.profile_last()
         a_.append(a)
