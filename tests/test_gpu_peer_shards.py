@@ -31,7 +31,7 @@ def run_peer(buf, fmt, sps, thr, world, max_rounds=None):
     n = len(buf)
     L = n // world
     assert L * world == n
-    isz = buf.dtype.itemsize
+    isz = buf.dtype.itemsize * (buf.shape[1] if buf.ndim == 2 else 1)      # bytes per item (int16 / uint8 IQ: two components)
     ctxs = [g.Context(sps, L) for _ in range(world)]
     ptrs = []
     for r in range(world):
@@ -173,3 +173,22 @@ def test_peer_errors():
     with pytest.raises(g.AdsbError):
         ctx.shard_write(ptr, 16, byte_offset=(8 << 16))   # outside the allocation
     ctx.close()
+
+
+@pytest.mark.parametrize("fmt", [g.FMT_SC16, g.FMT_CU8])
+def test_peer_shards_integer_formats(fmt):
+    """int16 / uint8 IQ shards (widened on the device) across the cuts: equal to the whole-buffer oracle on the widened samples."""
+    sps, world, L = 2, 4, 12288
+    n = L * world
+    d = synth.synth_numpy(n, sps=sps, n_bursts=int(n * 2e-3), seed=321)
+    ri = d["iq"].view(np.float32).reshape(-1, 2)
+    if fmt == g.FMT_SC16:
+        raw = np.clip(np.round(ri * 32768.0), -32768, 32767).astype(np.int16)
+        v = raw.astype(np.float32) * np.float32(2.0 ** -15)
+    else:
+        raw = np.clip(np.round(ri * 128.0 + 127.5), 0, 255).astype(np.uint8)
+        v = (raw.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 128)
+    x = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]).astype(np.float32)
+    hits, rounds = run_peer(raw, fmt, sps, 0.02, world)
+    assert len(hits) > 20
+    check_against_oracle(hits, x, sps, 0.02)
