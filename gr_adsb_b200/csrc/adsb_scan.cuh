@@ -5,9 +5,9 @@
 //   phase 1  HBM -> registers -> |IQ|^2 -> shared memory, threshold bitmap by warp ballot
 //   phase 2  bitmap -> falling edges -> pulse centres (bit-parallel for runs <= LMAX samples),
 //            dense 3-tap pre-filter, full 16-tap preamble test on the survivors
-//   phase 3  candidates in pairs, two tasks per pair spread over the warps: exact medians of the two 100-sample
-//            noise windows (one per half-warp: register sorting network + selection of the two middle ranks), and
-//            2 x 112 PPM decisions by ballot with CRC-24 by XOR-reduction; edge tiles: one warp per candidate
+//   phase 3  two kinds of task spread over the warps: exact medians of the 100-sample noise windows of four candidates
+//            (8 lanes and 16 keys per lane each: register sorting network + selection of the two middle ranks), and
+//            2 x 112 PPM decisions of a pair by ballot with CRC-24 by XOR-reduction; edge tiles: one warp per candidate
 // Interior tiles of the specialised sample rates (2, 4, 8 samples/symbol) take the fast paths; tiles
 // touching the window edges, and other rates, take a generic per-edge path with identical results.
 #pragma once
@@ -50,6 +50,7 @@ struct Geo {
     static constexpr int NV = (CW + 3 + 5 * H + 3) / 4;                // float4 loads of the dense pre-filter
     static_assert(SPS == 0 || (S % NT == 0 && RH >= 120 * SPS && RH % 32 == 0), "tile geometry");
     static_assert(CW % 4 == 0 && CW >= 12 && LB >= LMAX + 1 && T % 32 == 0, "chunk geometry");
+    static_assert(DB <= 4, "the dense pre-filter's register window starts 4 samples before the chunk (LMAX <= 9)");
 };
 
 __host__ __device__ inline int tile_items(int sps, int nt = kThreads) { return ((sps == 2 || sps == 4) ? ADSB_NCH2 * ADSB_CW : 2 * ADSB_CW8) * nt; }
@@ -331,44 +332,43 @@ __device__ __forceinline__ void slice_candidate(const ScanParams &P, Get get, lo
     if (lane < 4) rec.bits[lane] = pack_msb_first(lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3]);
 }
 
-// Two candidates of an interior tile per warp (lanes 0-15 / 16-31): full 100-sample noise window, burst
-// fully staged, so no edge cases.  mp = shared-memory address of the candidate's centre sample.  The work
-// of a pair is split into two independent roles taken by different warps: the noise median / SNR ratio,
-// and the PPM slice + CRC; they fill disjoint fields of the staged record.
-template <int SPS, int FMT>
-__device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float *mp, long long p, int lane,
+// Four candidates of an interior tile per warp (8 lanes each): the noise medians / SNR ratios.  Full 100-sample noise
+// window, burst fully staged, so no edge cases; mp = shared-memory address of the candidate's centre sample.
+template <int FMT>
+__device__ __forceinline__ void slice_quad_snr(const ScanParams &P, const float *mp, long long p, int lane,
                                                bool write, Rec &rec)
 {
-    const int hl = lane & 15;
-    unsigned k[8];
+    const int l8 = lane & 7;
+    unsigned k[16];
     bool nan = false;
     // 100 samples + 14 pads below everything + 14 pads above everything: the median's two order statistics
     // (ranks 49, 50 of 100) are ranks 63, 64 of the 128, the two middle ones
     constexpr int kLowPads = (128 - kNoise) / 2;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int e = r * 16 + hl;
+    for (int r = 0; r < 16; r++) {
+        const int e = r * 8 + l8;
         const float v = (e < kNoise) ? mp[e - kNoise] : 0.0f;
         if (FMT != kFmtF32) {
-            // |IQ|^2 computed here is never negative: the raw bits order like the values; NaN bits sort above +inf
             k[r] = (e < kNoise) ? __float_as_uint(v) : (e < kNoise + kLowPads ? 0u : 0x7f800000u);
         } else {
             nan |= (e < kNoise) && (v != v);
             k[r] = (e < kNoise) ? f2key(v) : (e < kNoise + kLowPads ? 0u : 0xffffffffu);
         }
     }
-    unsigned ka, kb, top;
-    half_mid128(k, lane, ka, kb, top);
+    unsigned lane_top;
+    const unsigned m = quarter_mid128(k, lane, lane_top);        // lanes 0-3 of the group: rank 63, lanes 4-7: rank 64
+    // |IQ|^2 computed in phase 1 is never negative, so NaN bits sort above +inf (the high pads): a NaN among the
+    // samples shows as some lane's largest key; a vote costs no shuffle
+    if (FMT != kFmtF32) nan = lane_top > 0x7f800000u;
+    const unsigned anyn = __ballot_sync(kFull, nan);
+    const unsigned mo = __shfl_xor_sync(kFull, m, 4);
     float med;
-    if (FMT != kFmtF32) {
-        med = __fmul_rn(__fadd_rn(__uint_as_float(ka), __uint_as_float(kb)), 0.5f);   // fl32(fl32(a+b)/2)
-        if (top > 0x7f800000u) med = __int_as_float(0x7fc00000);
-    } else {
-        const unsigned anyn = __ballot_sync(kFull, nan);
-        med = __fmul_rn(__fadd_rn(key2f(ka), key2f(kb)), 0.5f);
-        if ((anyn >> (lane & 16)) & 0xffffu) med = __int_as_float(0x7fc00000);
-    }
-    if (write && hl == 0) {
+    if (FMT != kFmtF32)
+        med = __fmul_rn(__fadd_rn(__uint_as_float(m), __uint_as_float(mo)), 0.5f);   // fl32(fl32(a+b)/2)
+    else
+        med = __fmul_rn(__fadd_rn(key2f(m), key2f(mo)), 0.5f);
+    if ((anyn >> (lane & 24)) & 0xffu) med = __int_as_float(0x7fc00000);
+    if (write && l8 == 0) {
         rec.idx = P.base + p;
         rec.snr = __fdiv_rn(mp[0], med);       // ratio; the compact kernel applies 10*log10(.)+1.6
     }
@@ -938,28 +938,8 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     const int sps_rt = SPS ? SPS : P.sps;
     // records go straight to this tile's block of the candidate array (the two tasks of a pair fill
     // disjoint fields), so no staging buffer and no barrier after the slicing
-    const int n_tasks = ((n_cand + 1) >> 1) * 2;
-    for (int t = wid; t < n_tasks; t += n_warps) {
-        const int c = (t >> 1) * 2;
-        const bool two = c + 1 < n_cand;
-        const unsigned e0 = sm.list[c];
-        const unsigned e1 = two ? sm.list[c + 1] : e0;
-        if (g_off + (unsigned)c + 1u >= P.cand_cap) {
-            if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
-            continue;
-        }
-        if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
-            const int kp = (lane & 16) ? (int)e1 : (int)e0;
-            const int cc = c + ((lane >> 4) & (two ? 1 : 0));
-            const bool wr = two || !(lane & 16);
-            Rec &rec = P.cand[g_off + cc];
-            if (t & 1)
-                slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, rec);
-            else
-                slice_pair_snr<SPS ? SPS : 2, FMT>(P, sm.mag + kp, w0 + kp, lane, wr, rec);
-            continue;
-        }
-        if (t & 1) continue;                            // generic path: the even task does both roles
+    // generic path of one pair (edge tiles, long runs, short noise windows): one warp per candidate, both roles
+    auto generic_pair = [&](int c, bool two, unsigned e0, unsigned e1) {
         unsigned crc_t[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
@@ -976,6 +956,41 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
                 slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
             }
         }
+    };
+    // interior tiles: first the noise medians of four candidates at a time (the long tasks: 8 lanes and 16 keys per lane
+    // each, so that most of the sorting network runs inside the lane -- the warp shuffles of the two-per-warp version
+    // were a quarter of this kernel's L1/shared data-pipe traffic), then the PPM slices of pairs (half-warp each); the two
+    // kinds of task fill disjoint fields of the record.  A pair that needs the generic path (long run, noise window
+    // leaving the staged span) is left to its slice task, which then does both roles; so is every pair of an edge tile.
+    const int n_quads = (SPS != 0 && fast) ? ((n_cand + 3) >> 2) : 0;
+    const int n_tasks = n_quads + ((n_cand + 1) >> 1);
+    for (int t = wid; t < n_tasks; t += n_warps) {
+        if (t < n_quads) {
+            const int c = 4 * t + (lane >> 3);
+            const bool have = c < n_cand;
+            const unsigned ec = sm.list[have ? c : 4 * t];
+            const unsigned ep = (have && (c ^ 1) < n_cand) ? sm.list[c ^ 1] : ec;
+            const bool wr = have && !((ec | ep) >> 15) && g_off + (unsigned)(c & ~1) + 1u < P.cand_cap;
+            const int kp = wr ? (int)ec : kLeftHalo;          // any staged slot with a full window below it
+            slice_quad_snr<FMT>(P, sm.mag + kp, w0 + kp, lane, wr, P.cand[g_off + (have ? c : 0)]);
+            continue;
+        }
+        const int c = (t - n_quads) * 2;
+        const bool two = c + 1 < n_cand;
+        const unsigned e0 = sm.list[c];
+        const unsigned e1 = two ? sm.list[c + 1] : e0;
+        if (g_off + (unsigned)c + 1u >= P.cand_cap) {
+            if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
+            continue;
+        }
+        if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
+            const int kp = (lane & 16) ? (int)e1 : (int)e0;
+            const int cc = c + ((lane >> 4) & (two ? 1 : 0));
+            const bool wr = two || !(lane & 16);
+            slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, P.cand[g_off + cc]);
+            continue;
+        }
+        generic_pair(c, two, e0, e1);
     }
 }
 

@@ -30,10 +30,10 @@ def _defs(*on):
 
 VARIANTS = {
     "default": _defs(),
-    "cw16": _defs() + ["-DADSB_CW=16"],     # 16-sample detect chunks (round-1 geometry: bank-conflicted pre-filter loads)
-    "cw8_16": _defs() + ["-DADSB_CW8=16"],  # 8 Msps / generic kernels with the round-1 chunk width
-    "cw12": _defs() + ["-DADSB_CW=12", "-DADSB_MIN_CTAS=8"],                     # 3072-sample tiles
-    "cw12x2": _defs() + ["-DADSB_CW=12", "-DADSB_NCH2=2", "-DADSB_MIN_CTAS=6"],  # 6144-sample tiles, two chunks per thread
+    # "cw16": _defs() + ["-DADSB_CW=16"],     # 16-sample detect chunks (round-1 geometry: bank-conflicted pre-filter loads)
+    # "cw8_16": _defs() + ["-DADSB_CW8=16"],  # 8 Msps / generic kernels with the round-1 chunk width
+    # "cw12": _defs() + ["-DADSB_CW=12", "-DADSB_MIN_CTAS=8"],                     # 3072-sample tiles
+    # "cw12x2": _defs() + ["-DADSB_CW=12", "-DADSB_NCH2=2", "-DADSB_MIN_CTAS=6"],  # 6144-sample tiles, two chunks per thread
     # latency path with %globaltimer stamps per phase (tools/latency_probe.py prints them)
     "timing": _defs() + ["-DADSB_SMALL_TIMING=1"],
 }
