@@ -385,6 +385,70 @@ __device__ __forceinline__ void warp_sort128(unsigned (&k)[4], int lane)
     }
 }
 
+// Two independent 128-key sets per warp: lanes 0-15 hold one, lanes 16-31 the other; 8 keys per lane, logical
+// position e = 8*(lane & 15) + r, same mirrored bitonic network as warp_sort128 (only the steps with a stride of 8
+// or more cross lanes, which is what makes slicing candidates in pairs cheaper than one per warp).
+// The two middle order statistics (ranks 63 and 64 of 128) of each set, without finishing the sort: sort the two
+// 64-key halves A (lanes 0-7) and B (lanes 8-15) with sizes 2..64 of the network, then use that
+// {min(A[i], B[63-i])} are exactly the 64 smallest keys and {max(A[i], B[63-i])} the 64 largest -- rank 63 is the
+// largest of the former, rank 64 the smallest of the latter.  Replaces the last 7 of 28 network steps by one
+// exchange and two reductions.  `top` = the largest key (last element of A or of B).
+__device__ __forceinline__ void half_mid128(unsigned (&k)[8], int lane, unsigned &lo_mid, unsigned &hi_mid, unsigned &top)
+{
+    // each lane's 8 keys ascending
+    // Batcher's odd-even merge sort of 8: 19 comparators instead of the bitonic network's 24
+    cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
+    cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+    cex(k[1], k[2]); cex(k[5], k[6]);
+    cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
+    cex(k[2], k[4]); cex(k[3], k[5]);
+    cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
+#pragma unroll
+    for (int size = 16; size <= 64; size <<= 1) {
+        {
+            const int lm = (size >> 3) - 1;
+            const bool lower = (lane & (size >> 4)) == 0;
+            unsigned o[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) o[r] = __shfl_xor_sync(kFull, k[7 - r], lm);
+#pragma unroll
+            for (int r = 0; r < 8; r++) k[r] = lower ? min(k[r], o[r]) : max(k[r], o[r]);
+        }
+#pragma unroll
+        for (int j = size >> 2; j >= 8; j >>= 1) {
+            const int lm = j >> 3;
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const unsigned o = __shfl_xor_sync(kFull, k[r], lm);
+                k[r] = lower ? min(k[r], o) : max(k[r], o);
+            }
+        }
+        cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
+        cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) cex(k[r], k[r + 1]);
+    }
+    // A = positions 0..63 (lanes 0-7 of the half-warp), B = 64..127 (lanes 8-15), both ascending
+    const unsigned ta = __shfl_sync(kFull, k[7], (lane & 16) | 7), tb = __shfl_sync(kFull, k[7], (lane & 16) | 15);
+    top = max(ta, tb);
+    const bool lower = (lane & 8) == 0;
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const unsigned o = __shfl_xor_sync(kFull, k[7 - r], 15);       // position e <-> 127 - e
+        const unsigned v = lower ? min(k[r], o) : max(k[r], o);
+        m = (r == 0) ? v : (lower ? max(m, v) : min(m, v));
+    }
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+        const unsigned o = __shfl_xor_sync(kFull, m, d);
+        m = lower ? max(m, o) : min(m, o);
+    }
+    lo_mid = __shfl_sync(kFull, m, lane & 16);
+    hi_mid = __shfl_sync(kFull, m, (lane & 16) | 8);
+}
+
 // Four independent 128-key sets per warp: lanes 8c .. 8c+7 hold set c, 16 keys per lane, logical position
 // e = 16*(lane & 7) + r, same mirrored bitonic network as warp_sort128.  Only the strides of 16 and more cross lanes:
 // 64 shuffles for four sets (two sets per warp with 8 keys per lane took 63 for two -- and the shuffles were a quarter

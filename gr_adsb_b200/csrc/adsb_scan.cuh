@@ -67,6 +67,17 @@ __host__ __device__ inline int right_halo(int sps, int nt = kThreads)
 constexpr int kTileSlots = 32;    // candidate records reserved per tile (typical busy tile: 5-10)
 constexpr int kSlowCap = 256;     // long-run falls deferred per tile before falling back to serial handling
 
+// Phase 3 takes the noise medians four candidates per warp where tiles usually hold several candidates, two per warp
+// otherwise.  Measured on the B200 (profiles/r02/variants_quad_median.jsonl, variants_median_policy.jsonl, bench lines):
+// 2 Msps, 10k bursts/s (8.7 candidates per 5120-sample tile): 0.460 ms against 0.483 ms; 8 Msps, 10k bursts/s (2.6 per
+// 6144-sample tile: a quad task mostly sorts pads): 0.474 ms against 0.444 ms.  One policy per kernel on purpose: a
+// build with both median routines in the same kernel, chosen per task, ran 3-8 % slower than either.
+#ifndef ADSB_QUAD_MEDIANS_SPS
+#define ADSB_QUAD_MEDIANS_SPS 2
+#endif
+template <int SPS>
+constexpr bool kQuadMedians = SPS == ADSB_QUAD_MEDIANS_SPS;
+
 // ---- shared-memory layout ------------------------------------------------------------------------
 struct TileSmem {
     float *mag;             // S
@@ -369,6 +380,47 @@ __device__ __forceinline__ void slice_quad_snr(const ScanParams &P, const float 
         med = __fmul_rn(__fadd_rn(key2f(m), key2f(mo)), 0.5f);
     if ((anyn >> (lane & 24)) & 0xffu) med = __int_as_float(0x7fc00000);
     if (write && l8 == 0) {
+        rec.idx = P.base + p;
+        rec.snr = __fdiv_rn(mp[0], med);       // ratio; the compact kernel applies 10*log10(.)+1.6
+    }
+}
+
+// The same for two candidates per warp (lanes 0-15 / 16-31, 8 keys per lane): cheaper than a quad task when only one
+// or two candidates are left over (330 instead of 550 instructions).
+template <int SPS, int FMT>
+__device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float *mp, long long p, int lane,
+                                               bool write, Rec &rec)
+{
+    const int hl = lane & 15;
+    unsigned k[8];
+    bool nan = false;
+    // 100 samples + 14 pads below everything + 14 pads above everything: the median's two order statistics
+    // (ranks 49, 50 of 100) are ranks 63, 64 of the 128, the two middle ones
+    constexpr int kLowPads = (128 - kNoise) / 2;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int e = r * 16 + hl;
+        const float v = (e < kNoise) ? mp[e - kNoise] : 0.0f;
+        if (FMT != kFmtF32) {
+            // |IQ|^2 computed here is never negative: the raw bits order like the values; NaN bits sort above +inf
+            k[r] = (e < kNoise) ? __float_as_uint(v) : (e < kNoise + kLowPads ? 0u : 0x7f800000u);
+        } else {
+            nan |= (e < kNoise) && (v != v);
+            k[r] = (e < kNoise) ? f2key(v) : (e < kNoise + kLowPads ? 0u : 0xffffffffu);
+        }
+    }
+    unsigned ka, kb, top;
+    half_mid128(k, lane, ka, kb, top);
+    float med;
+    if (FMT != kFmtF32) {
+        med = __fmul_rn(__fadd_rn(__uint_as_float(ka), __uint_as_float(kb)), 0.5f);   // fl32(fl32(a+b)/2)
+        if (top > 0x7f800000u) med = __int_as_float(0x7fc00000);
+    } else {
+        const unsigned anyn = __ballot_sync(kFull, nan);
+        med = __fmul_rn(__fadd_rn(key2f(ka), key2f(kb)), 0.5f);
+        if ((anyn >> (lane & 16)) & 0xffffu) med = __int_as_float(0x7fc00000);
+    }
+    if (write && hl == 0) {
         rec.idx = P.base + p;
         rec.snr = __fdiv_rn(mp[0], med);       // ratio; the compact kernel applies 10*log10(.)+1.6
     }
@@ -932,65 +984,108 @@ __device__ __forceinline__ void slice_tile(const ScanParams &P, const TileSmem &
     const unsigned g_off = (unsigned)sm.scratch[kScrOff];
 
     // ---- phase 3: per-candidate SNR ratio + PPM slice + CRC ----
-    // interior tiles: candidates go in pairs (half-warp each) and every pair is two tasks -- median/SNR and
-    // PPM slice/CRC -- spread over the eight warps; edges / long runs: one warp per candidate, both roles
     const Access<FMT> X{P, sm.mag, w0, S};
     const int sps_rt = SPS ? SPS : P.sps;
     // records go straight to this tile's block of the candidate array (the two tasks of a pair fill
     // disjoint fields), so no staging buffer and no barrier after the slicing
-    // generic path of one pair (edge tiles, long runs, short noise windows): one warp per candidate, both roles
-    auto generic_pair = [&](int c, bool two, unsigned e0, unsigned e1) {
-        unsigned crc_t[4];
+    // Two task layouts, one per kernel (see kQuadMedians): noise medians four candidates per warp + PPM slices of pairs,
+    // or both in pairs.
+    if constexpr (kQuadMedians<SPS>) {
+        // generic path of one pair (edge tiles, long runs, short noise windows): one warp per candidate, both roles
+        auto generic_pair = [&](int c, bool two, unsigned e0, unsigned e1) {
+            unsigned crc_t[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
-        for (int q = 0; q < (two ? 2 : 1); q++) {
-            const unsigned e = q ? e1 : e0;
-            const int kf = e & 0x7fff;
-            Rec &rec = P.cand[g_off + c + q];
-            if (e >> 15) {
-                long long p;
-                resolve_long<FMT>(P, sm, w0, kf, lane, p);
-                slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
-            } else {
-                const float *mp = sm.mag + kf;              // list holds the centre slot
-                slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
+            for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
+            for (int q = 0; q < (two ? 2 : 1); q++) {
+                const unsigned e = q ? e1 : e0;
+                const int kf = e & 0x7fff;
+                Rec &rec = P.cand[g_off + c + q];
+                if (e >> 15) {
+                    long long p;
+                    resolve_long<FMT>(P, sm, w0, kf, lane, p);
+                    slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
+                } else {
+                    const float *mp = sm.mag + kf;              // list holds the centre slot
+                    slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
+                }
+            }
+        };
+        // first the noise medians of four candidates at a time (the long tasks), then the PPM slices of pairs (half-warp
+        // each); the two kinds of task fill disjoint fields of the record.  A pair that needs the generic path (long run,
+        // noise window leaving the staged span) is left to its slice task, which then does both roles; so is every pair of
+        // an edge tile.
+        const int n_quads = (SPS != 0 && fast) ? ((n_cand + 3) >> 2) : 0;
+        const int n_tasks = n_quads + ((n_cand + 1) >> 1);
+        for (int t = wid; t < n_tasks; t += n_warps) {
+            if (t < n_quads) {
+                const int c = 4 * t + (lane >> 3);
+                const bool have = c < n_cand;
+                const unsigned ec = sm.list[have ? c : 4 * t];
+                const unsigned ep = (have && (c ^ 1) < n_cand) ? sm.list[c ^ 1] : ec;
+                const bool wr = have && !((ec | ep) >> 15) && g_off + (unsigned)(c & ~1) + 1u < P.cand_cap;
+                const int kp = wr ? (int)ec : kLeftHalo;          // any staged slot with a full window below it
+                slice_quad_snr<FMT>(P, sm.mag + kp, w0 + kp, lane, wr, P.cand[g_off + (have ? c : 0)]);
+                continue;
+            }
+            const int c = (t - n_quads) * 2;
+            const bool two = c + 1 < n_cand;
+            const unsigned e0 = sm.list[c];
+            const unsigned e1 = two ? sm.list[c + 1] : e0;
+            if (g_off + (unsigned)c + 1u >= P.cand_cap) {
+                if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
+                continue;
+            }
+            if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
+                const int kp = (lane & 16) ? (int)e1 : (int)e0;
+                const int cc = c + ((lane >> 4) & (two ? 1 : 0));
+                const bool wr = two || !(lane & 16);
+                slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, P.cand[g_off + cc]);
+                continue;
+            }
+            generic_pair(c, two, e0, e1);
+        }
+    } else {
+        // interior tiles: candidates go in pairs (half-warp each) and every pair is two tasks -- median/SNR and PPM
+        // slice/CRC -- spread over the eight warps; edges / long runs: one warp per candidate, both roles
+        const int n_tasks = ((n_cand + 1) >> 1) * 2;
+        for (int t = wid; t < n_tasks; t += n_warps) {
+            const int c = (t >> 1) * 2;
+            const bool two = c + 1 < n_cand;
+            const unsigned e0 = sm.list[c];
+            const unsigned e1 = two ? sm.list[c + 1] : e0;
+            if (g_off + (unsigned)c + 1u >= P.cand_cap) {
+                if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
+                continue;
+            }
+            if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
+                const int kp = (lane & 16) ? (int)e1 : (int)e0;
+                const int cc = c + ((lane >> 4) & (two ? 1 : 0));
+                const bool wr = two || !(lane & 16);
+                Rec &rec = P.cand[g_off + cc];
+                if (t & 1)
+                    slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, rec);
+                else
+                    slice_pair_snr<SPS ? SPS : 2, FMT>(P, sm.mag + kp, w0 + kp, lane, wr, rec);
+                continue;
+            }
+            if (t & 1) continue;                            // generic path: the even task does both roles
+            unsigned crc_t[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) crc_t[j] = (j * 32 + lane < kMsgBits) ? P.crc_tab[j * 32 + lane] : 0u;
+            for (int q = 0; q < (two ? 2 : 1); q++) {
+                const unsigned e = q ? e1 : e0;
+                const int kf = e & 0x7fff;
+                Rec &rec = P.cand[g_off + c + q];
+                if (e >> 15) {
+                    long long p;
+                    resolve_long<FMT>(P, sm, w0, kf, lane, p);
+                    slice_candidate(P, [&X, p](int d) { return X(p + d); }, p, sps_rt, h, lane, crc_t, false, rec);
+                } else {
+                    const float *mp = sm.mag + kf;              // list holds the centre slot
+                    slice_candidate(P, [mp](int d) { return mp[d]; }, w0 + kf, sps_rt, h, lane, crc_t, fast, rec);
+                }
             }
         }
-    };
-    // interior tiles: first the noise medians of four candidates at a time (the long tasks: 8 lanes and 16 keys per lane
-    // each, so that most of the sorting network runs inside the lane -- the warp shuffles of the two-per-warp version
-    // were a quarter of this kernel's L1/shared data-pipe traffic), then the PPM slices of pairs (half-warp each); the two
-    // kinds of task fill disjoint fields of the record.  A pair that needs the generic path (long run, noise window
-    // leaving the staged span) is left to its slice task, which then does both roles; so is every pair of an edge tile.
-    const int n_quads = (SPS != 0 && fast) ? ((n_cand + 3) >> 2) : 0;
-    const int n_tasks = n_quads + ((n_cand + 1) >> 1);
-    for (int t = wid; t < n_tasks; t += n_warps) {
-        if (t < n_quads) {
-            const int c = 4 * t + (lane >> 3);
-            const bool have = c < n_cand;
-            const unsigned ec = sm.list[have ? c : 4 * t];
-            const unsigned ep = (have && (c ^ 1) < n_cand) ? sm.list[c ^ 1] : ec;
-            const bool wr = have && !((ec | ep) >> 15) && g_off + (unsigned)(c & ~1) + 1u < P.cand_cap;
-            const int kp = wr ? (int)ec : kLeftHalo;          // any staged slot with a full window below it
-            slice_quad_snr<FMT>(P, sm.mag + kp, w0 + kp, lane, wr, P.cand[g_off + (have ? c : 0)]);
-            continue;
-        }
-        const int c = (t - n_quads) * 2;
-        const bool two = c + 1 < n_cand;
-        const unsigned e0 = sm.list[c];
-        const unsigned e1 = two ? sm.list[c + 1] : e0;
-        if (g_off + (unsigned)c + 1u >= P.cand_cap) {
-            if (lane == 0) atomicOr(&P.hdr->flags, kFlagCandOverflow);
-            continue;
-        }
-        if (SPS != 0 && fast && !((e0 | e1) >> 15)) {
-            const int kp = (lane & 16) ? (int)e1 : (int)e0;
-            const int cc = c + ((lane >> 4) & (two ? 1 : 0));
-            const bool wr = two || !(lane & 16);
-            slice_pair_bits<SPS ? SPS : 2>(P, sm.mag + kp, lane, wr, P.cand[g_off + cc]);
-            continue;
-        }
-        generic_pair(c, two, e0, e1);
     }
 }
 

@@ -34,6 +34,7 @@ VARIANTS = {
     # "cw8_16": _defs() + ["-DADSB_CW8=16"],  # 8 Msps / generic kernels with the round-1 chunk width
     # "cw12": _defs() + ["-DADSB_CW=12", "-DADSB_MIN_CTAS=8"],                     # 3072-sample tiles
     # "cw12x2": _defs() + ["-DADSB_CW=12", "-DADSB_NCH2=2", "-DADSB_MIN_CTAS=6"],  # 6144-sample tiles, two chunks per thread
+    "paironly": _defs() + ["-DADSB_QUAD_MEDIANS_SPS=-1"],   # phase-3 medians two candidates per warp at every rate
     # latency path with %globaltimer stamps per phase (tools/latency_probe.py prints them)
     "timing": _defs() + ["-DADSB_SMALL_TIMING=1"],
 }
@@ -127,10 +128,18 @@ def check_one(name, log2n, iters):
     out["parity"]["golden"] = {"ok": gold_ok, "cases": gold_n}
     out["ok"] = out["ok"] and gold_ok
 
-    # ---- timing: the bench workload (2 Msps, 5e-3 bursts/sample), 2^log2n samples resident in HBM ----
+    # ---- timing: the bench workload (2 Msps, 5e-3 bursts/sample) and BASELINE configs[2] (8 Msps, 1.25e-3),
+    # 2^log2n samples resident in HBM ----
+    for key, sps, dens in (("timing", 2, 5e-3), ("timing_sps8", 8, 1.25e-3)):
+        out[key] = time_one(g, synth, sps, dens, log2n, iters)
+    return out
+
+
+def time_one(g, synth, sps, dens, log2n, iters):
+    import numpy as np
     n = 1 << log2n
     seg = 1 << min(log2n, 24)
-    d = synth.synth_numpy(seg, sps=2, n_bursts=int(seg * 5e-3), seed=1090)
+    d = synth.synth_numpy(seg, sps=sps, n_bursts=int(seg * dens), seed=1090)
     host = np.ascontiguousarray(d["iq"])
     rt = None
     if os.environ.get("ADSB_VARIANT_HOSTMEM") == "1":
@@ -145,23 +154,21 @@ def check_one(name, log2n, iters):
             except OSError:
                 continue
         if rt is None:
-            out["timing"] = "libcudart not found"
-            return out
+            return "libcudart not found"
         rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         rt.cudaFree.argtypes = [C.c_void_p]
         dev = C.c_void_p()
         if rt.cudaMalloc(C.byref(dev), n * 8 + 256) != 0:
-            out["timing"] = "cudaMalloc failed"
-            return out
+            return "cudaMalloc failed"
         for r in range(n // seg):
             assert rt.cudaMemcpy(C.c_void_p(dev.value + r * seg * 8), host.ctypes.data_as(C.c_void_p), seg * 8, 1) == 0
         assert rt.cudaDeviceSynchronize() == 0
-    ctx = g.Context(2, n)
+    ctx = g.Context(sps, n)
     ctx.profile_enable(True)
     scan, res = [], []
     for it in range(iters + 3):
-        ctx.burst_work_dev(dev.value, 1, n, n, 15, 0.01)
+        ctx.burst_work_dev(dev.value, 1, n, n, 8 * sps - 1, 0.01)
         a, b = ctx.profile_last()
         if it >= 3:
             scan.append(a)
@@ -169,13 +176,13 @@ def check_one(name, log2n, iters):
     cnt, _ = ctx.burst_finish(fetch_hits=False)
     scan.sort()
     res.sort()
-    out["timing"] = {"log2n": log2n, "iters": iters, "scan_ms_median": scan[len(scan) // 2], "scan_ms_min": scan[0],
-                     "resolve_ms_median": res[len(res) // 2], "gbs_median": n * 8 / max(scan[len(scan) // 2], 1e-9) / 1e6,
-                     "hits": cnt["n_hits"], "candidates": cnt["n_candidates"], "crc_ok": cnt["n_crc_ok"]}
+    t = {"log2n": log2n, "iters": iters, "scan_ms_median": scan[len(scan) // 2], "scan_ms_min": scan[0],
+         "resolve_ms_median": res[len(res) // 2], "gbs_median": n * 8 / max(scan[len(scan) // 2], 1e-9) / 1e6,
+         "hits": cnt["n_hits"], "candidates": cnt["n_candidates"], "crc_ok": cnt["n_crc_ok"]}
     ctx.close()
     if rt is not None:
         rt.cudaFree(dev)
-    return out
+    return t
 
 
 def run(names, log2n, iters, write_best=True):
