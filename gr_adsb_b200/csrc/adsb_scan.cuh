@@ -385,8 +385,8 @@ __device__ __forceinline__ void slice_quad_snr(const ScanParams &P, const float 
     }
 }
 
-// The same for two candidates per warp (lanes 0-15 / 16-31, 8 keys per lane): cheaper than a quad task when only one
-// or two candidates are left over (330 instead of 550 instructions).
+// The same for two candidates per warp (lanes 0-15 / 16-31, 8 keys per lane): 330 instead of 550 instructions per task,
+// the cheaper routine where a tile rarely holds more than two or three candidates (kernels of the other sample rates).
 template <int SPS, int FMT>
 __device__ __forceinline__ void slice_pair_snr(const ScanParams &P, const float *mp, long long p, int lane,
                                                bool write, Rec &rec)
