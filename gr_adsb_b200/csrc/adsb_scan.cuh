@@ -33,7 +33,7 @@ namespace adsb {
 #endif
 
 // ---- compile-time geometry per samples-per-symbol and CTA size -------------------------------------------
-// NT = threads per CTA (256 in the shipped build; 128 / 512 exist for A/B builds, ADSB_SCAN_NT_VARIANTS).  A thread
+// NT = threads per CTA (256; 128- and 512-thread CTAs measured slower in round 2, profiles/r02/variants_call1.jsonl).  A thread
 // owns one 20-sample chunk of the tile (two 12-sample chunks at 8 Msps and unspecialised rates), so the tile grows with the CTA.
 template <int SPS, int NT = kThreads>
 struct Geo {
